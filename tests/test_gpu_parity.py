@@ -1,0 +1,368 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA engine, called through the C ABI, against
+  (1) the golden vectors produced by the unmodified reference (tests/golden/*.npz) and
+  (2) the float64 numpy oracle on the same seeded inputs.
+
+Stated tolerance (north_star: "within a stated fp32 tolerance"): the engine computes in fp32 with FFMA and a
+different summation order than torch's CPU GEMMs, so single-step quantities are compared at rtol 2e-4 / atol 2e-5
+(losses, Q values, log-probs), gradients at rtol 1e-3 / atol 5e-6, one-Adam-step parameters at atol 2e-6
+(|dp| = lr = 3e-4), and short trajectories at a few lr (Adam's g/sqrt(v) amplifies sign flips of ~0 gradients).
+Integer / byte work (ring pointer arithmetic, gather, index sets) is bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_helpers import GOLDEN, assert_close, batch_from, load_case, summary
+from oracle import sac_numpy as onp
+from oracle.sac_numpy import ACTOR_KEYS, CRITIC_KEYS
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine_for(g, actor, critic, arrays, hp, K=None, flags=0):
+    from torch_actor_critic_b200.engine import Engine, actor_views, critic_views
+    O, A, B = int(g["obs_dim"]), int(g["act_dim"]), int(g["batch"])
+    H = [int(h) for h in g["hidden"]]
+    K = K or int(g["n_updates"])
+    eng = Engine(O, A, H, batch_size=B, max_burst=K, device=0, act_limit=hp.act_limit, flags=flags)
+    pa, pc = eng.new_actor_arena(), eng.new_critic_arena()
+    av, cv = actor_views(eng.layout, pa, O, A, H), critic_views(eng.layout, pc, O, A, H)
+    for k in ACTOR_KEYS:
+        av[k].copy_(torch.from_numpy(actor[k]))
+    for k in CRITIC_KEYS:
+        cv[k].copy_(torch.from_numpy(critic[k]))
+    pt = pc.clone()
+    tv = critic_views(eng.layout, pt, O, A, H)
+    eng.bind_params(pa, pc, pt)
+    adam = [eng.new_actor_arena(), eng.new_actor_arena(), eng.new_critic_arena(), eng.new_critic_arena()]
+    eng.bind_adam(adam[0], adam[1], 0, adam[2], adam[3], 0)
+    dev = eng.tdev()
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in arrays.items()}
+    eng.bind_buffer(t["state"], t["actions"], t["rewards"], t["next_state"], t["done"])
+    eng.set_buffer_state(0, len(arrays["rewards"]))
+    return eng, av, cv, tv, adam
+
+
+def _check(g, prefix, name, value, rtol, atol):
+    value = np.asarray(value)
+    if f"{prefix}.{name}" in g:
+        assert_close(value, g[f"{prefix}.{name}"], rtol, atol, f"{prefix}.{name}")
+    else:
+        s, a, sub = summary(value)
+        assert_close(sub, g[f"{prefix}.{name}.sub"], rtol, atol, f"{prefix}.{name}.sub")
+        assert abs(s - float(g[f"{prefix}.{name}.sum"])) <= atol * value.size + rtol * float(g[f"{prefix}.{name}.abssum"])
+
+
+@pytest.mark.parametrize("name", ["small", "ragged", "c1"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_update_matches_reference_golden(name, mode):
+    from torch_actor_critic_b200.engine import actor_views, critic_views
+    g, actor, critic, arrays, hp = load_case(name)
+    eng, av, cv, tv, adam = _engine_for(g, actor, critic, arrays, hp)
+    eng.set_mode(mode)
+    O, A = int(g["obs_dim"]), int(g["act_dim"])
+    H = [int(h) for h in g["hidden"]]
+    K = int(g["n_updates"])
+    # ---- first update: every intermediate of sac/algorithm.py:61-72,37-41 ----
+    lq, lp = eng.update(1, idx=g["idx"][:1], eps=g["eps"][:1])
+    assert_close(lq.cpu().numpy(), g["loss_q"][:1], 2e-4, 2e-5, "loss_q[0]")
+    assert_close(lp.cpu().numpy(), g["loss_pi"][:1], 2e-4, 2e-5, "loss_pi[0]")
+    for key in ("a2", "logp_next", "q1_target", "q2_target", "backup", "q1", "q2", "pi", "logp_pi", "q1_pi", "q2_pi"):
+        assert_close(eng.debug_read(key), g[f"step0.{key}"], 2e-4, 5e-5, key)
+    ga = actor_views(eng.layout, torch.from_numpy(eng.debug_read("grad_actor")), O, A, H)
+    gc = critic_views(eng.layout, torch.from_numpy(eng.debug_read("grad_critic")), O, A, H)
+    for k in ACTOR_KEYS:
+        _check(g, "step0.actor_grads", k, ga[k].numpy(), 1e-3, 5e-6)
+    for k in CRITIC_KEYS:
+        _check(g, "step0.critic_grads", k, gc[k].numpy(), 1e-3, 5e-6)
+    for k in ACTOR_KEYS:
+        _check(g, "step0.actor", k, av[k].cpu().numpy(), 1e-6, 2e-6)
+    for k in CRITIC_KEYS:
+        _check(g, "step0.critic", k, cv[k].cpu().numpy(), 1e-6, 2e-6)
+        _check(g, "step0.target", k, tv[k].cpu().numpy(), 1e-6, 1e-7)
+    # ---- remaining updates in one burst ----
+    if K > 1:
+        lq, lp = eng.update(K - 1, idx=g["idx"][1:], eps=g["eps"][1:])
+        assert_close(lq.cpu().numpy(), g["loss_q"][1:], 1e-3, 1e-4, "loss_q[1:]")
+        assert_close(lp.cpu().numpy(), g["loss_pi"][1:], 1e-3, 1e-4, "loss_pi[1:]")
+    for k in ACTOR_KEYS:
+        _check(g, "final.actor", k, av[k].cpu().numpy(), 1e-5, 3e-4 * K)
+    for k in CRITIC_KEYS:
+        _check(g, "final.critic", k, cv[k].cpu().numpy(), 1e-5, 3e-4 * K)
+        _check(g, "final.target", k, tv[k].cpu().numpy(), 1e-5, 3e-4 * K * 0.005 * K + 1e-6)
+    assert eng.adam_steps() == (K, K)
+    assert eng.launch_count() > 0
+
+
+def test_persistent_and_phased_modes_bit_identical():
+    g, actor, critic, arrays, hp = load_case("ragged")
+    outs = []
+    for mode in (0, 1):
+        eng, av, cv, tv, adam = _engine_for(g, actor, critic, arrays, hp)
+        eng.set_mode(mode)
+        lq, lp = eng.update(int(g["n_updates"]), idx=g["idx"], eps=g["eps"])
+        torch.cuda.synchronize()
+        outs.append((lq.cpu(), lp.cpu(), eng._keep["actor"].cpu(), eng._keep["critic"].cpu(), eng._keep["target"].cpu()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_adam_moments_match_reference():
+    from torch_actor_critic_b200.engine import actor_views, critic_views
+    g, actor, critic, arrays, hp = load_case("small")
+    eng, av, cv, tv, adam = _engine_for(g, actor, critic, arrays, hp)
+    O, A, H = int(g["obs_dim"]), int(g["act_dim"]), [int(h) for h in g["hidden"]]
+    eng.update(int(g["n_updates"]), idx=g["idx"], eps=g["eps"])
+    ma, va = actor_views(eng.layout, adam[0], O, A, H), actor_views(eng.layout, adam[1], O, A, H)
+    mc = critic_views(eng.layout, adam[2], O, A, H)
+    for k in ACTOR_KEYS:
+        assert_close(ma[k].cpu().numpy(), g[f"final.pi_opt.exp_avg.{k}"], 2e-3, 2e-6, k)
+        assert_close(va[k].cpu().numpy(), g[f"final.pi_opt.exp_avg_sq.{k}"], 4e-3, 1e-9, k)
+    for k in CRITIC_KEYS:
+        assert_close(mc[k].cpu().numpy(), g[f"final.q_opt.exp_avg.{k}"], 2e-3, 2e-6, k)
+
+
+def test_canonical_logprob_flag_matches_oracle():
+    """SACB_FLAG_CANONICAL_LOGPROB: the parenthesised correction (not what the reference computes)."""
+    from torch_actor_critic_b200 import _lib
+    g, actor, critic, arrays, hp = load_case("small")
+    hp.logprob_reference_form = False
+    eng, av, cv, tv, adam = _engine_for(g, actor, critic, arrays, hp, flags=_lib.FLAG_CANONICAL_LOGPROB)
+    lq, lp = eng.update(1, idx=g["idx"][:1], eps=g["eps"][:1])
+    a64, c64, t64 = (onp.cast_params(p, np.float64) for p in (actor, critic, critic))
+    o = onp.sac_update(a64, c64, t64, onp.AdamState.zeros_like(a64), onp.AdamState.zeros_like(c64),
+                       batch_from(arrays, g["idx"][0], np.float64), g["eps"][0, 0].astype(np.float64),
+                       g["eps"][0, 1].astype(np.float64), hp)
+    assert_close(lq.cpu().numpy(), [o["loss_q"]], 2e-4, 2e-5)
+    assert_close(lp.cpu().numpy(), [o["loss_pi"]], 2e-4, 2e-5)
+    assert abs(float(lp) - float(g["loss_pi"][0])) > 1e-2          # and it does differ from the reference form
+
+
+def test_piecewise_api_equals_burst():
+    """SAC.update_critic / update_policy / update_targets on an explicit Batch == the fused burst (same arithmetic)."""
+    import torch.optim as optim
+    from torch_actor_critic_b200.buffer.replay_buffer import Batch
+    from torch_actor_critic_b200.networks.linear import Actor, DoubleCritic
+    from torch_actor_critic_b200.sac.algorithm import SAC, update_targets
+    from copy import deepcopy
+    g, actor_np, critic_np, arrays, hp = load_case("small")
+    O, A, B = int(g["obs_dim"]), int(g["act_dim"]), int(g["batch"])
+    H = [int(h) for h in g["hidden"]]
+    actor = Actor(O, A, H, act_limit=hp.act_limit)
+    critic = DoubleCritic(O, A, H)
+    actor.load_state_dict({k: torch.tensor(v) for k, v in actor_np.items()})
+    critic.load_state_dict({k: torch.tensor(v) for k, v in critic_np.items()})
+    target = deepcopy(critic)
+    assert isinstance(target, DoubleCritic) and target.arena.data_ptr() != critic.arena.data_ptr()
+    pi_opt = optim.Adam(actor.parameters(), lr=3e-4)
+    q_opt = optim.Adam(critic.parameters(), lr=3e-4)
+    sac = SAC(alpha=0.2, gamma=0.99, polyak=0.995, reward_scale=1.0, epochs=1, batch_size=B, start_steps=0,
+              steps_per_epoch=1, max_ep_len=1, update_after=0, update_every=4, save_every=1)
+    for k in range(int(g["n_updates"])):
+        b = batch_from(arrays, g["idx"][k])
+        samples = Batch(*(torch.tensor(b[n]).cuda() for n in ("states", "actions", "rewards", "next_states", "done")))
+        lq = sac.update_critic(q_opt, actor, critic, target, samples, eps=g["eps"][k, 0])
+        lp = sac.update_policy(pi_opt, actor, critic, samples, eps=g["eps"][k, 1])
+        update_targets(critic, target, sac.polyak)
+        assert lq.dim() == 0 and lp.dim() == 0
+        assert_close(lq.cpu().numpy(), g["loss_q"][k], 1e-3, 1e-4, "loss_q")
+        assert_close(lp.cpu().numpy(), g["loss_pi"][k], 1e-3, 1e-4, "loss_pi")
+    sd_a, sd_c, sd_t = actor.state_dict(), critic.state_dict(), target.state_dict()
+    K = int(g["n_updates"])
+    for k in ACTOR_KEYS:
+        assert_close(sd_a[k].cpu().numpy(), g[f"final.actor.{k}"], 1e-5, 3e-4 * K, k)
+    for k in CRITIC_KEYS:
+        assert_close(sd_c[k].cpu().numpy(), g[f"final.critic.{k}"], 1e-5, 3e-4 * K, k)
+        assert_close(sd_t[k].cpu().numpy(), g[f"final.target.{k}"], 1e-5, 1e-5, k)
+    # optimizer state is visible to torch (checkpoint path, sac/algorithm.py:176-178)
+    st = q_opt.state_dict()["state"]
+    assert len(st) == 12 and float(st[0]["step"]) == K
+    assert_close(st[0]["exp_avg"].cpu().numpy(), g["final.q_opt.exp_avg.q1.layers.0.weight"], 2e-3, 2e-6)
+    assert float(pi_opt.state_dict()["state"][0]["step"]) == K
+
+
+def test_forward_modules_match_reference():
+    """Actor / DoubleCritic forward contracts incl. the reference's own shape tests (tests/test_linear.py:7-41)."""
+    from torch_actor_critic_b200.networks.linear import Actor, Critic, DoubleCritic
+    g, _, _, _, hp = load_case("small")
+    O, A = int(g["obs_dim"]), int(g["act_dim"])
+    H = [int(h) for h in g["hidden"]]
+    actor = Actor(O, A, H, act_limit=hp.act_limit)
+    critic = DoubleCritic(O, A, H)
+    actor.load_state_dict({k: torch.tensor(g[f"final.actor.{k}"]) for k in ACTOR_KEYS})
+    critic.load_state_dict({k: torch.tensor(g[f"final.critic.{k}"]) for k in CRITIC_KEYS})
+    x = torch.tensor(g["fwd.x"])
+    pi, logp = actor(x, deterministic=True)
+    assert_close(pi.cpu().numpy(), g["fwd.pi_det"], 1e-4, 1e-5)
+    assert_close(logp.cpu().numpy(), g["fwd.logp_det"], 1e-4, 5e-5)
+    pn, none = actor(x, deterministic=True, with_logprob=False)
+    assert none is None and torch.equal(pn, pi)
+    pu, lu = actor(x[0], deterministic=True)
+    assert list(pu.size()) == [A] and list(lu.size()) == []
+    assert_close(pu.cpu().numpy(), g["fwd.pi_unbatched"], 1e-4, 1e-5)
+    q1, q2 = critic(x, torch.tensor(g["fwd.act"]))
+    assert_close(q1.cpu().numpy(), g["fwd.q1"], 1e-4, 1e-5)
+    assert_close(q2.cpu().numpy(), g["fwd.q2"], 1e-4, 1e-5)
+    # stochastic path: injected eps reproduces the oracle; device-drawn eps is ~N(0,1)
+    eps = torch.randn(4, A)
+    p2, l2 = actor(x, eps=eps)
+    ao = {k: g[f"final.actor.{k}"] for k in ACTOR_KEYS}
+    po, lo, _ = onp.actor_forward(ao, g["fwd.x"], eps.numpy(), hp)
+    assert_close(p2.cpu().numpy(), po, 1e-4, 1e-5)
+    assert_close(l2.cpu().numpy(), lo, 1e-4, 5e-5)
+    # the reference's shape tests, verbatim sizes
+    a = Actor(10, 20, [256, 256])
+    p, lp = a(torch.ones((10,)))
+    assert list(p.size()) == [20] and list(lp.size()) == []
+    c = Critic(5, 10, [256, 256])
+    assert list(c(torch.ones((2, 5)), torch.ones((2, 10))).size()) == [2]
+    dc = DoubleCritic(5, 10, [256, 256])
+    v1, v2 = dc(torch.ones((3, 5)), torch.ones((3, 10)))
+    assert list(v1.size()) == [3] and list(v2.size()) == [3]
+    # more rows than one kernel pass (chunking) and a 1000-row batch
+    big = torch.randn(1000, 10)
+    pb, lb = a(big, deterministic=True)
+    ps, ls = a(big[300:301], deterministic=True)
+    assert pb.shape == (1000, 20) and torch.allclose(pb[300], ps[0]) and torch.allclose(lb[300], ls[0])
+
+
+def test_replay_buffer_matches_reference_bit_exact():
+    """store ring semantics + gather vs the reference's ReplayBuffer (golden replay_buffer.npz)."""
+    import os
+    from torch_actor_critic_b200.buffer.replay_buffer import Batch, ReplayBuffer
+    g = dict(np.load(os.path.join(GOLDEN, "replay_buffer.npz")))
+    buf = ReplayBuffer(int(g["n"]), int(g["obs_dim"]), int(g["act_dim"]))
+    for i in range(int(g["n_store"])):
+        buf.store(g["in.state"][i], g["in.actions"][i], g["in.rewards"][i], g["in.next_state"][i], g["in.done"][i])
+        assert buf.size == g["sizes"][i] and buf.ptr == g["ptrs"][i]
+    for k in ("state", "actions", "rewards", "next_state", "done"):
+        assert np.array_equal(getattr(buf, k).cpu().numpy(), g[f"final.{k}"]), k
+    b = buf.sample(int(g["batch"]), idx=g["idx"])
+    assert isinstance(b, Batch)
+    for k in ("states", "actions", "rewards", "next_states", "done"):
+        v = getattr(b, k)
+        assert v.dtype == torch.float32 and np.array_equal(v.cpu().numpy(), g[f"batch.{k}"]), k
+    with pytest.raises(ValueError):
+        ReplayBuffer(4, 3, 2).sample(1)                          # empty buffer, as random.sample raises
+    with pytest.raises(ValueError):
+        buf.sample(int(g["n"]) + 1)
+    # vectorised store == repeated store (wrap included)
+    buf2 = ReplayBuffer(int(g["n"]), int(g["obs_dim"]), int(g["act_dim"]))
+    buf2.store_many(g["in.state"], g["in.actions"], g["in.rewards"], g["in.next_state"], g["in.done"])
+    for k in ("state", "actions", "rewards", "next_state", "done"):
+        assert np.array_equal(getattr(buf2, k).cpu().numpy(), g[f"final.{k}"]), k
+    assert (buf2.ptr, buf2.size) == (buf.ptr, buf.size)
+
+
+def test_device_sampler_without_replacement_and_uniform():
+    from torch_actor_critic_b200.buffer.replay_buffer import ReplayBuffer
+    n, B = 300, 256
+    buf = ReplayBuffer(n, 2, 1, seed=3)
+    obs = np.arange(n, dtype=np.float32)[:, None].repeat(2, 1)
+    buf.store_many(obs, np.zeros((n, 1), np.float32), np.arange(n, dtype=np.float32), obs, np.zeros(n, bool))
+    counts = np.zeros(n)
+    for _ in range(200):
+        b = buf.sample(B)
+        r = b.rewards.cpu().numpy().astype(int)
+        assert len(np.unique(r)) == B                           # duplicate-free, like random.sample
+        assert np.array_equal(b.states.cpu().numpy()[:, 0].astype(int), r)      # rows stay together
+        counts[r] += 1
+    expect = 200 * B / n
+    assert np.all(np.abs(counts - expect) < 6 * np.sqrt(expect * (1 - B / n)) + 1)   # uniform inclusion probability
+    full = buf.sample(n)                                          # B == size: a permutation
+    assert np.array_equal(np.sort(full.rewards.cpu().numpy()), np.arange(n))
+
+
+def _c1_setup(N=1_000_000, seed=0):
+    from torch_actor_critic_b200.engine import Engine, actor_views, critic_views
+    O, A, H, B = 17, 6, [256, 256], 256
+    rng = np.random.default_rng(seed)
+    actor, critic = onp.init_params(O, A, H, rng)
+    eng = Engine(O, A, H, batch_size=B, max_burst=50, device=0, act_limit=1.0, seed=seed)
+    dev = eng.tdev()
+    pa, pc = eng.new_actor_arena(), eng.new_critic_arena()
+    for k, v in actor_views(eng.layout, pa, O, A, H).items():
+        v.copy_(torch.from_numpy(actor[k]))
+    for k, v in critic_views(eng.layout, pc, O, A, H).items():
+        v.copy_(torch.from_numpy(critic[k]))
+    pt = pc.clone()
+    eng.bind_params(pa, pc, pt)
+    eng.bind_adam(eng.new_actor_arena(), eng.new_actor_arena(), 0, eng.new_critic_arena(), eng.new_critic_arena(), 0)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    s = torch.randn(N, O, device=dev, generator=gen); s2 = torch.randn(N, O, device=dev, generator=gen)
+    a = torch.rand(N, A, device=dev, generator=gen) * 2 - 1; r = torch.randn(N, device=dev, generator=gen)
+    d = torch.rand(N, device=dev, generator=gen) < 1e-3
+    eng.bind_buffer(s, a, r, s2, d)
+    eng.set_buffer_state(0, N)
+    return eng, pa, pc, pt
+
+
+def test_full_size_c1_properties():
+    """BASELINE config 1 (1e6-transition HBM buffer, B=256, MLP 256x256): size-independent properties."""
+    eng, pa, pc, pt = _c1_setup()
+    pc0, pt0, pa0 = pc.clone(), pt.clone(), pa.clone()
+    lq, lp = eng.update(1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(lq).all() and torch.isfinite(lp).all()
+    # Polyak identity (sac/algorithm.py:80-81) holds exactly in fp32: targ' = fl(fl(0.995*targ) + fl(0.005*critic'))
+    pk, pcf = torch.tensor(0.995, dtype=torch.float32).cuda(), torch.tensor(1.0 - 0.995, dtype=torch.float32).cuda()
+    assert torch.equal(pt, pt0 * pk + pcf * pc)
+    # first Adam step moves every parameter with a non-zero gradient by lr (bias-corrected m/sqrt(v) = sign(g))
+    gc = torch.from_numpy(eng.debug_read("grad_critic")).cuda()
+    nz = gc.abs() > 1e-12
+    assert torch.allclose((pc - pc0)[nz].abs(), torch.full_like(pc[nz], 3e-4), rtol=1e-3)
+    assert torch.equal((pc - pc0)[nz].sign(), -gc[nz].sign())
+    ga = torch.from_numpy(eng.debug_read("grad_actor")).cuda()
+    nza = ga.abs() > 1e-12
+    assert torch.allclose((pa - pa0)[nza].abs(), torch.full_like(pa[nza], 3e-4), rtol=1e-3)
+    # a 50-update burst with device-drawn indices and noise: finite, and deterministic for a fixed seed
+    lq1, lp1 = eng.update(50)
+    eng2, pa2, pc2, pt2 = _c1_setup()
+    eng2.update(1)
+    lq2, lp2 = eng2.update(50)
+    torch.cuda.synchronize()
+    assert torch.isfinite(lq1).all() and torch.isfinite(lp1).all()
+    assert torch.equal(lq1, lq2) and torch.equal(lp1, lp2) and torch.equal(pc, pc2) and torch.equal(pa, pa2)
+
+
+def test_full_size_c1_first_update_matches_oracle():
+    """One update at BASELINE config-1 sizes with injected indices/noise vs the float64 oracle."""
+    eng, pa, pc, pt = _c1_setup(N=200_000, seed=1)
+    from torch_actor_critic_b200.engine import actor_views, critic_views
+    O, A, H, B = 17, 6, [256, 256], 256
+    rng = np.random.default_rng(5)
+    idx = rng.choice(200_000, B, replace=False)[None]
+    eps = rng.standard_normal((1, 2, B, A)).astype(np.float32)
+    s, a, r, s2, d = (t.cpu().numpy() for t in eng._keep["buf"])
+    actor = {k: v.cpu().numpy().astype(np.float64) for k, v in actor_views(eng.layout, pa, O, A, H).items()}
+    critic = {k: v.cpu().numpy().astype(np.float64) for k, v in critic_views(eng.layout, pc, O, A, H).items()}
+    target = onp.cast_params(critic, np.float64)
+    lq, lp = eng.update(1, idx=idx, eps=eps)
+    batch = dict(states=s[idx[0]].astype(np.float64), actions=a[idx[0]].astype(np.float64), rewards=r[idx[0]].astype(np.float64),
+                 next_states=s2[idx[0]].astype(np.float64), done=d[idx[0]].astype(np.float64))
+    hp = onp.HyperParams(act_limit=1.0)
+    o = onp.sac_update(actor, critic, target, onp.AdamState.zeros_like(actor), onp.AdamState.zeros_like(critic), batch,
+                       eps[0, 0].astype(np.float64), eps[0, 1].astype(np.float64), hp)
+    assert_close(lq.cpu().numpy(), [o["loss_q"]], 1e-4, 1e-5, "loss_q")
+    assert_close(lp.cpu().numpy(), [o["loss_pi"]], 1e-4, 1e-5, "loss_pi")
+    for key in ("backup", "q1", "q2", "logp_next", "logp_pi", "q1_pi", "q2_pi"):
+        assert_close(eng.debug_read(key), o[key], 2e-4, 5e-5, key)
+    gc = critic_views(eng.layout, torch.from_numpy(eng.debug_read("grad_critic")), O, A, H)
+    for k in CRITIC_KEYS:
+        assert_close(gc[k].numpy(), o["critic_grads"][k], 1e-3, 5e-6, k)
+    ga = actor_views(eng.layout, torch.from_numpy(eng.debug_read("grad_actor")), O, A, H)
+    for k in ACTOR_KEYS:
+        assert_close(ga[k].numpy(), o["actor_grads"][k], 1e-3, 5e-6, k)
+
+
+def test_errors_are_loud():
+    from torch_actor_critic_b200 import _lib
+    from torch_actor_critic_b200.engine import Engine
+    eng = Engine(3, 2, [8, 8], batch_size=4, max_burst=2, device=0)
+    with pytest.raises(_lib.SacbError) as ei:
+        eng.update(1)
+    assert ei.value.code == _lib.SACB_ERR_STATE
+    with pytest.raises(NotImplementedError):
+        Engine(3, 2, [8, 8, 8])
+    with pytest.raises(_lib.SacbError):
+        Engine(3, 2, [8, 8], flags=_lib.FLAG_PI_FROM_STATES)

@@ -1,0 +1,1069 @@
+// sacb_engine.cu -- host side of libsacb200.so: engine state, phase-program builder, launches and the C ABI
+// declared in include/sacb200.h.  Compile: nvcc -gencode arch=compute_100a,code=sm_100a (see __graft_entry__.build).
+#include "sacb_device.cuh"
+
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sacb200.h"
+
+using namespace sacb;
+
+// ------------------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(SACB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// minimal NCCL binding (dlopen; declarations restated from the public nccl.h API)
+// ------------------------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl(const char* path) {
+    if (g_nccl.lib) return 0;
+    const char* cands[] = {path, "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* c : cands) {
+        if (!c || !*c) continue;
+        lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(SACB_ERR_NCCL, "dlopen libnccl failed: %s", dlerror());
+    g_nccl.lib = lib;
+#define SYM(field, name)                                                               \
+    *(void**)(&g_nccl.field) = dlsym(lib, name);                                       \
+    if (!g_nccl.field) return fail(SACB_ERR_NCCL, "libnccl misses symbol %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(Broadcast, "ncclBroadcast");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return 0;
+}
+#define NC(call)                                                                                          \
+    do {                                                                                                  \
+        int r_ = (call);                                                                                  \
+        if (r_ != 0) return fail(SACB_ERR_NCCL, "%s: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+    } while (0)
+constexpr int kNcclFloat = 7, kNcclSum = 0;
+
+// ------------------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------------------
+static inline long long r4(long long x) { return (x + 3) & ~3LL; }
+
+struct ProgRange { int begin = 0, end = 0; };
+
+struct sacb_engine {
+    sacb_config cfg{};
+    sacb_layout_info lay{};
+    int num_sms = 0, grid_coop = 0;
+    int mode = 0;
+    long long launches = 0;
+    // bound arenas
+    float *pa = nullptr, *pc = nullptr, *pt = nullptr;
+    float *ma = nullptr, *va = nullptr, *mc = nullptr, *vc = nullptr;
+    long long step_pi = 0, step_q = 0;
+    float *bs = nullptr, *ba = nullptr, *br = nullptr, *bs2 = nullptr;
+    uint8_t* bd = nullptr;
+    long long cap = 0, ptr = 0, size = 0;
+    // workspace
+    float* ws = nullptr;
+    size_t ws_floats = 0;
+    int ldx = 0, lds = 0, ldh = 0, lddpi = 0, tnH2 = 0, row_tiles = 0;
+    float *xs, *xp, *x2, *s2buf, *rd, *ah1, *ah2, *heads, *logp, *ch1, *ch2, *th1, *th2, *qpart, *qtpart, *qbuf, *qfw,
+        *dh2, *dh1, *dpi, *ghead, *adh2, *adh1, *lparts_q, *lparts_pi, *loss_scalar, *ga, *gc;
+    long long* idx_buf = nullptr;
+    float* eps_buf = nullptr;
+    unsigned long long* barrier = nullptr;
+    unsigned long long rng_counter = 0;
+    // programs
+    bool dirty = true;
+    std::vector<Job> jobs;
+    std::vector<Phase> phases;
+    Job* d_jobs = nullptr;
+    Phase* d_phases = nullptr;
+    size_t d_jobs_cap = 0, d_phases_cap = 0;
+    ProgRange p_update, p_policy, p_targets, p_actor_fwd, p_critic_fwd[2];
+    int ph_crit_begin = 0, ph_crit_adam = 0, ph_pi_begin = 0, ph_pi_adam = 0;   // split points inside p_update
+    // store staging
+    uint8_t* stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t stage_ev = nullptr;
+    // comm
+    nccl_comm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+static void compute_layout(const sacb_config& c, sacb_layout_info& L) {
+    const long long O = c.obs_dim, A = c.act_dim, H1 = c.hidden1, H2 = c.hidden2;
+    long long o = 0;
+    L.actor_w0 = o; o = r4(o + H1 * O);
+    L.actor_b0 = o; o = r4(o + H1);
+    L.actor_w1 = o; o = r4(o + H2 * H1);
+    L.actor_b1 = o; o = r4(o + H2);
+    L.actor_w_mu = o; L.actor_w_ls = o + A * H2; o = r4(o + 2 * A * H2);     // [mu ; log_std] form one [2A,H2] matrix
+    L.actor_b_mu = o; L.actor_b_ls = o + A; o = r4(o + 2 * A);
+    L.actor_floats = o;
+    o = 0;
+    const long long W0 = H1 * (O + A);
+    L.critic_w0[0] = o; L.critic_w0[1] = o + W0; o = r4(o + 2 * W0);         // twin layer-0 weights form one [2H1,O+A] matrix
+    L.critic_b0[0] = o; L.critic_b0[1] = o + H1; o = r4(o + 2 * H1);
+    L.critic_w1[0] = o; L.critic_w1[1] = o + H2 * H1; o = r4(o + 2 * H2 * H1);
+    L.critic_b1[0] = o; L.critic_b1[1] = o + H2; o = r4(o + 2 * H2);
+    L.critic_w2[0] = o; L.critic_w2[1] = o + H2; o = r4(o + 2 * H2);
+    L.critic_b2[0] = o; L.critic_b2[1] = o + 1; o = r4(o + 2);
+    L.critic_floats = o;
+}
+
+static int check_cfg(const sacb_config* c) {
+    if (!c) return fail(SACB_ERR_INVALID, "null config");
+    if (c->struct_size != sizeof(sacb_config)) return fail(SACB_ERR_INVALID, "sacb_config size mismatch (ABI): got %u want %zu", c->struct_size, sizeof(sacb_config));
+    if (c->obs_dim < 1 || c->act_dim < 1 || c->hidden1 < 1 || c->hidden2 < 1) return fail(SACB_ERR_INVALID, "dims must be positive");
+    if (c->batch_size < 1 || c->batch_size > 65536) return fail(SACB_ERR_INVALID, "batch_size out of range");
+    if (c->max_burst < 1) return fail(SACB_ERR_INVALID, "max_burst must be >= 1");
+    if (c->flags & SACB_FLAG_PI_FROM_STATES) return fail(SACB_ERR_INVALID, "SACB_FLAG_PI_FROM_STATES is not implemented");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// program builder
+// ------------------------------------------------------------------------------------------------------------
+struct Builder {
+    sacb_engine* e;
+    std::vector<Job>& jobs;
+    std::vector<Phase>& phases;
+    int cur = -1;
+    explicit Builder(sacb_engine* e_) : e(e_), jobs(e_->jobs), phases(e_->phases) {}
+    int phase() {
+        Phase p{(int)jobs.size(), 0, 0, 0};
+        phases.push_back(p);
+        cur = (int)phases.size() - 1;
+        return cur;
+    }
+    void add(Job j) {
+        Phase& p = phases[cur];
+        j.tile_begin = p.ntiles;
+        p.ntiles += j.ntiles;
+        p.job_count += 1;
+        jobs.push_back(j);
+    }
+    static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+    static Job zero() { Job j; memset(&j, 0, sizeof j); j.nz = 1; return j; }
+    // C[M,N] = epi( sum_r A(i,r) B(j,r) )
+    Job gemm(int mode, int epi, const float* A, int lda, long long sA, const float* B, int ldb, long long sB, float* C,
+             int ldc, long long sC, int M, int N, int K, int nz, int dyn = 0) {
+        Job j = zero();
+        j.type = J_GEMM; j.mode = mode; j.epi = epi;
+        j.A = A; j.lda = lda; j.sA = sA; j.B = B; j.ldb = ldb; j.sB = sB; j.C = C; j.ldc = ldc; j.sC = sC;
+        j.M = M; j.N = N; j.K = K; j.nz = nz; j.rows_dynamic = dyn;
+        j.a_vec = al16(A) && (lda % 4 == 0) && (sA % 4 == 0);
+        j.b_vec = al16(B) && (ldb % 4 == 0) && (sB % 4 == 0);
+        j.ntiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN) * nz;
+        return j;
+    }
+    Job colsum(const float* X, int ldx, long long sX, const float* w, long long sW, float* out, long long sOut, int M, int N, int nz) {
+        Job j = zero();
+        j.type = J_COLSUM; j.A = X; j.lda = ldx; j.sA = sX; j.aux0 = w; j.sAux = sW; j.C = out; j.sC = sOut;
+        j.M = M; j.N = N; j.nz = nz; j.ntiles = ((N + 31) / 32) * nz;
+        return j;
+    }
+};
+
+static void build_programs(sacb_engine* e) {
+    e->jobs.clear();
+    e->phases.clear();
+    Builder b(e);
+    const sacb_config& c = e->cfg;
+    const sacb_layout_info& L = e->lay;
+    const int O = c.obs_dim, A = c.act_dim, H1 = c.hidden1, H2 = c.hidden2, B = c.batch_size;
+    const int OA = O + A, ldx = e->ldx, lds = e->lds, ldh = e->ldh, lddpi = e->lddpi;
+    float *PA = e->pa, *PC = e->pc, *PT = e->pt, *GA = e->ga, *GC = e->gc;
+    const long long sW1 = L.critic_w1[1] - L.critic_w1[0];
+    const int row_tiles = e->row_tiles;
+
+    auto actor_l0 = [&](int dyn) {
+        Job j = b.gemm(G_FWD, E_BIAS_RELU, e->s2buf, lds, 0, PA + L.actor_w0, O, 0, e->ah1, H1, 0, B, H1, O, 1, dyn);
+        j.bias = PA + L.actor_b0; return j; };
+    auto actor_l1 = [&](int dyn) {
+        Job j = b.gemm(G_FWD, E_BIAS_RELU, e->ah1, H1, 0, PA + L.actor_w1, H1, 0, e->ah2, H2, 0, B, H2, H1, 1, dyn);
+        j.bias = PA + L.actor_b1; return j; };
+    auto actor_heads = [&](int dyn) {
+        Job j = b.gemm(G_FWD, E_BIAS, e->ah2, H2, 0, PA + L.actor_w_mu, H2, 0, e->heads, ldh, 0, B, 2 * A, H2, 1, dyn);
+        j.bias = PA + L.actor_b_mu; return j; };
+    auto row_heads = [&](int dyn) {
+        Job j = Builder::zero();
+        j.type = J_ROW_HEADS; j.A = e->heads; j.lda = ldh; j.M = B; j.rows_dynamic = dyn;
+        j.out0 = e->x2; j.out1 = e->logp; j.out2 = e->xp; j.out3 = e->logp + B; j.ldc = ldx; j.i0 = O;
+        j.ntiles = (B + 7) / 8; return j; };
+    auto critic_l0 = [&](float* P, const float* X, float* H, int dyn) {
+        Job j = b.gemm(G_FWD, E_BIAS_RELU, X, ldx, 0, P + L.critic_w0[0], OA, 0, H, 2 * H1, 0, B, 2 * H1, OA, 1, dyn);
+        j.bias = P + L.critic_b0[0]; return j; };
+    auto critic_l1 = [&](float* P, const float* Hin, float* Hout, float* part, int dyn) {
+        Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, Hin, 2 * H1, H1, P + L.critic_w1[0], H1, sW1, Hout, 2 * H2, H2, B, H2, H1, 2, dyn);
+        j.bias = P + L.critic_b1[0]; j.sBias = H2; j.aux0 = P + L.critic_w2[0]; j.sAux = H2; j.out0 = part; j.i0 = B;
+        return j; };
+    auto critic_dx1 = [&]() {       // dh1 = (dh2 . W1) * relu'(h1)
+        Job j = b.gemm(G_DX, E_MASK, e->dh2, 2 * H2, H2, PC + L.critic_w1[0], H1, sW1, e->dh1, 2 * H1, H1, B, H1, H2, 2);
+        j.mask = e->ch1; j.ldmask = 2 * H1; j.sMask = H1; return j; };
+
+    // ---------------- full update: sample/gather -> update_critic -> update_policy -> update_targets ----------------
+    e->p_update.begin = (int)e->phases.size();
+    {   // P0 gather (ReplayBuffer.sample, buffer/replay_buffer.py:45-54)
+        b.phase();
+        Job j = Builder::zero();
+        j.type = J_GATHER; j.M = B; j.C = e->xs; j.out0 = e->xp; j.out1 = e->x2; j.ldc = ldx; j.out2 = e->s2buf; j.ldb = lds;
+        j.out3 = e->rd; j.ntiles = (B + 7) / 8;
+        b.add(j);
+    }
+    e->ph_crit_begin = (int)e->phases.size();
+    b.phase(); b.add(actor_l0(0)); b.add(critic_l0(PC, e->xs, e->ch1, 0));                 // P1
+    b.phase(); b.add(actor_l1(0)); b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0));      // P2
+    b.phase(); b.add(actor_heads(0));                                                       // P3
+    b.phase(); b.add(row_heads(0));                                                         // P4
+    b.phase(); b.add(critic_l0(PT, e->x2, e->th1, 0));                                      // P5 target critic on (s', a2)
+    b.phase(); b.add(critic_l1(PT, e->th1, e->th2, e->qtpart, 0));                          // P6
+    {   // P7 backup + dq + dh2 (sac/algorithm.py:63-72)
+        b.phase();
+        Job j = Builder::zero();
+        j.type = J_ROW_BACKUP; j.M = B; j.A = e->qpart; j.B = e->qtpart; j.i0 = B; j.i1 = e->tnH2;
+        j.bias = PC + L.critic_b2[0]; j.aux0 = PT + L.critic_b2[0]; j.aux1 = PC + L.critic_w2[0];
+        j.mask = e->ch2; j.ldmask = 2 * H2; j.C = e->dh2; j.ldc = 2 * H2; j.out0 = e->qbuf; j.out1 = e->lparts_q;
+        j.out2 = e->logp; j.aux2 = e->rd; j.aux3 = e->rd + B; j.ntiles = row_tiles;
+        b.add(j);
+    }
+    {   // P8 critic layer-1 grads + dh1
+        b.phase();
+        b.add(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2));
+        b.add(critic_dx1());
+        b.add(b.colsum(e->dh2, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, B, 2 * H2, 1));
+        b.add(b.colsum(e->ch2, 2 * H2, H2, e->qbuf + 5 * (size_t)B, B, GC + L.critic_w2[0], H2, B, H2, 2));
+    }
+    {   // P9 critic layer-0 grads, loss
+        b.phase();
+        b.add(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1));
+        b.add(b.colsum(e->dh1, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, B, 2 * H1, 1));
+        Job j = Builder::zero();
+        j.type = J_REDUCE_Q; j.A = e->lparts_q; j.i0 = row_tiles; j.out0 = e->loss_scalar; j.out1 = GC + L.critic_b2[0];
+        j.out2 = GC + L.critic_b2[1]; j.ntiles = 1;
+        b.add(j);
+    }
+    e->ph_crit_adam = (int)e->phases.size();
+    {   // P10 Adam(critic) [+ Polyak]
+        b.phase();
+        Job j = Builder::zero();
+        j.type = J_ADAM; j.C = PC; j.A = GC; j.out0 = e->mc; j.out1 = e->vc; j.out2 = PT; j.K = (int)L.critic_floats; j.i0 = 1;
+        j.ntiles = (int)((L.critic_floats + kThreads * 4 - 1) / (kThreads * 4));
+        b.add(j);
+    }
+    auto policy_tail = [&]() {
+        b.phase(); b.add(critic_l0(PC, e->xp, e->ch1, 0));                                  // critic on (s, pi)
+        b.phase(); b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0));
+        {
+            b.phase();
+            Job j = Builder::zero();
+            j.type = J_ROW_PI; j.M = B; j.A = e->qpart; j.i0 = B; j.i1 = e->tnH2; j.bias = PC + L.critic_b2[0];
+            j.aux1 = PC + L.critic_w2[0]; j.mask = e->ch2; j.ldmask = 2 * H2; j.C = e->dh2; j.ldc = 2 * H2;
+            j.out0 = e->qbuf; j.out1 = e->lparts_pi; j.aux2 = e->logp + B; j.ntiles = row_tiles;
+            b.add(j);
+        }
+        b.phase(); b.add(critic_dx1());
+        b.phase();      // dpi = dh1 . W0[:, O:O+A]   (both critics at once: reduction over 2*H1)
+        b.add(b.gemm(G_DX, E_STORE, e->dh1, 2 * H1, 0, PC + L.critic_w0[0] + O, OA, 0, e->dpi, lddpi, 0, B, A, 2 * H1, 1));
+        {
+            b.phase();
+            Job j = Builder::zero();
+            j.type = J_ROW_GHEAD; j.M = B; j.A = e->heads; j.lda = ldh; j.B = e->dpi; j.ldb = lddpi; j.C = e->ghead; j.ldc = ldh;
+            j.ntiles = (B + 15) / 16;
+            b.add(j);
+        }
+        {
+            b.phase();
+            b.add(b.gemm(G_DW, E_STORE, e->ghead, ldh, 0, e->ah2, H2, 0, GA + L.actor_w_mu, H2, 0, 2 * A, H2, B, 1));
+            b.add(b.colsum(e->ghead, ldh, 0, nullptr, 0, GA + L.actor_b_mu, 0, B, 2 * A, 1));
+            Job j = b.gemm(G_DX, E_MASK, e->ghead, ldh, 0, PA + L.actor_w_mu, H2, 0, e->adh2, H2, 0, B, H2, 2 * A, 1);
+            j.mask = e->ah2; j.ldmask = H2;
+            b.add(j);
+        }
+        {
+            b.phase();
+            b.add(b.gemm(G_DW, E_STORE, e->adh2, H2, 0, e->ah1, H1, 0, GA + L.actor_w1, H1, 0, H2, H1, B, 1));
+            b.add(b.colsum(e->adh2, H2, 0, nullptr, 0, GA + L.actor_b1, 0, B, H2, 1));
+            Job j = b.gemm(G_DX, E_MASK, e->adh2, H2, 0, PA + L.actor_w1, H1, 0, e->adh1, H1, 0, B, H1, H2, 1);
+            j.mask = e->ah1; j.ldmask = H1;
+            b.add(j);
+        }
+        {
+            b.phase();
+            b.add(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->s2buf, lds, 0, GA + L.actor_w0, O, 0, H1, O, B, 1));
+            b.add(b.colsum(e->adh1, H1, 0, nullptr, 0, GA + L.actor_b0, 0, B, H1, 1));
+            Job j = Builder::zero();
+            j.type = J_REDUCE_PI; j.A = e->lparts_pi; j.i0 = row_tiles; j.out0 = e->loss_scalar + 1; j.ntiles = 1;
+            b.add(j);
+        }
+        int adam_phase = b.phase();
+        {
+            Job j = Builder::zero();
+            j.type = J_ADAM; j.C = PA; j.A = GA; j.out0 = e->ma; j.out1 = e->va; j.out2 = nullptr; j.K = (int)L.actor_floats; j.i0 = 0;
+            j.ntiles = (int)((L.actor_floats + kThreads * 4 - 1) / (kThreads * 4));
+            b.add(j);
+        }
+        return adam_phase;
+    };
+    e->ph_pi_begin = (int)e->phases.size();
+    e->ph_pi_adam = policy_tail();
+    e->p_update.end = (int)e->phases.size();
+
+    // ---------------- standalone update_policy (actor trunk recomputed) ----------------
+    e->p_policy.begin = (int)e->phases.size();
+    b.phase(); b.add(actor_l0(0));
+    b.phase(); b.add(actor_l1(0));
+    b.phase(); b.add(actor_heads(0));
+    b.phase(); b.add(row_heads(0));
+    policy_tail();
+    e->p_policy.end = (int)e->phases.size();
+
+    // ---------------- update_targets ----------------
+    e->p_targets.begin = (int)e->phases.size();
+    {
+        b.phase();
+        Job j = Builder::zero();
+        j.type = J_POLYAK; j.C = PT; j.A = PC; j.K = (int)L.critic_floats;
+        j.ntiles = (int)((L.critic_floats + kThreads * 4 - 1) / (kThreads * 4));
+        b.add(j);
+    }
+    e->p_targets.end = (int)e->phases.size();
+
+    // ---------------- forward-only programs (dynamic row count) ----------------
+    e->p_actor_fwd.begin = (int)e->phases.size();
+    b.phase(); b.add(actor_l0(1));
+    b.phase(); b.add(actor_l1(1));
+    b.phase(); b.add(actor_heads(1));
+    b.phase(); b.add(row_heads(1));
+    e->p_actor_fwd.end = (int)e->phases.size();
+    for (int w = 0; w < 2; ++w) {
+        float* P = w ? PT : PC;
+        e->p_critic_fwd[w].begin = (int)e->phases.size();
+        b.phase(); b.add(critic_l0(P, e->xs, e->ch1, 1));
+        b.phase(); b.add(critic_l1(P, e->ch1, e->ch2, e->qpart, 1));
+        {
+            b.phase();
+            Job j = Builder::zero();
+            j.type = J_ROW_QSUM; j.M = B; j.rows_dynamic = 1; j.A = e->qpart; j.i0 = B; j.i1 = e->tnH2;
+            j.bias = P + L.critic_b2[0]; j.out0 = e->qfw; j.ntiles = (B + kThreads - 1) / kThreads;
+            b.add(j);
+        }
+        e->p_critic_fwd[w].end = (int)e->phases.size();
+    }
+}
+
+static int upload_programs(sacb_engine* e, cudaStream_t st) {
+    if (!e->dirty) return 0;
+    build_programs(e);
+    if (e->jobs.size() > e->d_jobs_cap) {
+        if (e->d_jobs) CU(cudaFree(e->d_jobs));
+        e->d_jobs_cap = e->jobs.size() + 16;
+        CU(cudaMalloc(&e->d_jobs, e->d_jobs_cap * sizeof(Job)));
+    }
+    if (e->phases.size() > e->d_phases_cap) {
+        if (e->d_phases) CU(cudaFree(e->d_phases));
+        e->d_phases_cap = e->phases.size() + 16;
+        CU(cudaMalloc(&e->d_phases, e->d_phases_cap * sizeof(Phase)));
+    }
+    // synchronous copies: the tables are rebuilt only on (re)bind
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(e->d_jobs, e->jobs.data(), e->jobs.size() * sizeof(Job), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_phases, e->phases.data(), e->phases.size() * sizeof(Phase), cudaMemcpyHostToDevice));
+    e->dirty = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small standalone kernels: RNG draws, dense batch load, sample gather
+// ------------------------------------------------------------------------------------------------------------
+// Duplicate-free uniform indices (random.sample(range(size), B), buffer/replay_buffer.py:46).  One CTA per update.
+// Every position draws from its own Philox subsequence; a position that collides with an EARLIER position redraws
+// (next counter of its subsequence) until the batch is duplicate free.  The procedure only compares values for
+// equality, so the result is uniform over ordered duplicate-free B-tuples.
+__global__ void __launch_bounds__(256) draw_indices_kernel(long long* __restrict__ out, int B, long long size,
+                                                           unsigned long long seed, unsigned long long counter0) {
+    extern __shared__ long long cand[];
+    __shared__ int any_dup;
+    const unsigned long long u = counter0 + blockIdx.x;
+    auto draw = [&](int i, int round) -> long long {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (u << 20) + (unsigned long long)i, (unsigned long long)round, &st);
+        uint4 r = curand4(&st);
+        unsigned long long x = ((unsigned long long)r.x << 32) | r.y;
+        return (long long)__umul64hi(x, (unsigned long long)size);
+    };
+    for (int i = threadIdx.x; i < B; i += blockDim.x) cand[i] = draw(i, 0);
+    __syncthreads();
+    for (int round = 1; round < 64; ++round) {
+        if (threadIdx.x == 0) any_dup = 0;
+        __syncthreads();
+        long long redraw_mask = 0;       // up to 64 positions per thread (B <= 16384)
+        int q = 0;
+        for (int i = threadIdx.x; i < B; i += blockDim.x, ++q) {
+            const long long v = cand[i];
+            bool dup = false;
+            for (int j = 0; j < i; ++j) dup |= (cand[j] == v);
+            if (dup) { redraw_mask |= (1LL << q); any_dup = 1; }
+        }
+        __syncthreads();
+        if (!any_dup) break;
+        q = 0;
+        for (int i = threadIdx.x; i < B; i += blockDim.x, ++q)
+            if (redraw_mask & (1LL << q)) cand[i] = draw(i, round);
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < B; i += blockDim.x) out[(size_t)blockIdx.x * B + i] = cand[i];
+}
+
+// Standard normal noise for Normal.rsample (networks/linear.py:45): 4 values per thread, Philox + Box-Muller.
+__global__ void draw_normal_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long counter0) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long base = t * 4;
+    if (base >= n) return;
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed ^ 0x9E3779B97F4A7C15ULL, counter0 + (unsigned long long)t, 0ULL, &st);
+    float4 v = curand_normal4(&st);
+    float vals[4] = {v.x, v.y, v.z, v.w};
+    for (int i = 0; i < 4 && base + i < n; ++i) out[base + i] = vals[i];
+}
+
+// Dense batch (the reference's Batch dataclass, buffer/replay_buffer.py:8-14) -> staging tiles.
+__global__ void load_batch_kernel(const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ r,
+                                  const float* __restrict__ s2, const float* __restrict__ d, int B, int O, int A, float* xs,
+                                  float* xp, float* x2, float* s2buf, float* rd, int ldx, int lds) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= B) return;
+    for (int c = lane; c < O; c += 32) {
+        float v = s[(size_t)m * O + c], w = s2[(size_t)m * O + c];
+        xs[(size_t)m * ldx + c] = v; xp[(size_t)m * ldx + c] = v; x2[(size_t)m * ldx + c] = w; s2buf[(size_t)m * lds + c] = w;
+    }
+    for (int c = lane; c < A; c += 32) xs[(size_t)m * ldx + O + c] = a[(size_t)m * A + c];
+    if (lane == 0) { rd[m] = r[m]; rd[B + m] = d[m]; }
+}
+
+// ReplayBuffer.sample gather into dense user arrays (buffer/replay_buffer.py:48-54).  Warp per row.
+__global__ void sample_gather_kernel(const long long* __restrict__ idx, int B, int O, int A, const float* __restrict__ bs,
+                                     const float* __restrict__ ba, const float* __restrict__ br, const float* __restrict__ bs2,
+                                     const unsigned char* __restrict__ bd, float* s, float* a, float* r, float* s2, float* d,
+                                     long long* idx_out) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= B) return;
+    const long long row = idx[m];
+    for (int c = lane; c < O; c += 32) { s[(size_t)m * O + c] = bs[(size_t)row * O + c]; s2[(size_t)m * O + c] = bs2[(size_t)row * O + c]; }
+    for (int c = lane; c < A; c += 32) a[(size_t)m * A + c] = ba[(size_t)row * A + c];
+    if (lane == 0) { r[m] = br[row]; d[m] = bd[row] ? 1.f : 0.f; if (idx_out) idx_out[m] = row; }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------------------
+static void fill_args(sacb_engine* e, RunArgs& ra) {
+    memset(&ra, 0, sizeof ra);
+    const sacb_config& c = e->cfg;
+    ra.jobs = e->d_jobs; ra.phases = e->d_phases;
+    ra.barrier = e->barrier;
+    ra.buf_state = e->bs; ra.buf_actions = e->ba; ra.buf_rewards = e->br; ra.buf_next_state = e->bs2; ra.buf_done = e->bd;
+    ra.alpha = c.alpha; ra.gamma = c.gamma; ra.polyak = c.polyak; ra.reward_scale = c.reward_scale;
+    ra.log_min_std = c.log_min_std; ra.log_max_std = c.log_max_std; ra.act_limit = c.act_limit;
+    ra.lr_pi = c.lr_pi; ra.lr_q = c.lr_q; ra.beta1 = c.beta1; ra.beta2 = c.beta2; ra.adam_eps = c.adam_eps;
+    ra.step_pi = e->step_pi; ra.step_q = e->step_q;
+    ra.grad_div = (float)e->world;
+    ra.flags = c.flags;
+    ra.O = c.obs_dim; ra.A = c.act_dim; ra.H1 = c.hidden1; ra.H2 = c.hidden2; ra.B = c.batch_size;
+    ra.pass_mask = 3;
+}
+
+// Run phases [pb, pe) for updates [kb, ke).  Cooperative persistent launch unless mode==1 or a single phase.
+static int run_phases(sacb_engine* e, RunArgs ra, int pb, int pe, int kb, int ke, cudaStream_t st) {
+    if (pe <= pb || ke <= kb) return 0;
+    const bool single = (pe - pb == 1) && (ke - kb == 1);
+    if (e->mode == 1 || single) {
+        for (int k = kb; k < ke; ++k)
+            for (int p = pb; p < pe; ++p) {
+                ra.phase_begin = p; ra.phase_end = p + 1; ra.k_begin = k; ra.k_end = k + 1; ra.use_barrier = 0;
+                int nt = e->phases[p].ntiles;
+                int grid = nt < 1 ? 1 : nt;
+                sac_phase_kernel<<<grid, kThreads, kSmemBytes, st>>>(ra);
+                CU(cudaGetLastError());
+                e->launches++;
+            }
+        return 0;
+    }
+    ra.phase_begin = pb; ra.phase_end = pe; ra.k_begin = kb; ra.k_end = ke; ra.use_barrier = 1;
+    CU(cudaMemsetAsync(e->barrier, 0, sizeof(unsigned long long), st));
+    void* args[] = {&ra};
+    CU(cudaLaunchCooperativeKernel((void*)sac_phase_kernel, dim3(e->grid_coop), dim3(kThreads), args, kSmemBytes, st));
+    e->launches++;
+    return 0;
+}
+
+static int need(bool cond, const char* what) { return cond ? 0 : fail(SACB_ERR_STATE, "%s not bound", what); }
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int sacb_abi_version(void) { return SACB_ABI_VERSION; }
+const char* sacb_last_error(void) { return g_err.c_str(); }
+
+int sacb_layout(const sacb_config* cfg, sacb_layout_info* out) {
+    if (int r = check_cfg(cfg)) return r;
+    if (!out) return fail(SACB_ERR_INVALID, "null out");
+    compute_layout(*cfg, *out);
+    return 0;
+}
+
+int sacb_create(const sacb_config* cfg, sacb_handle* out) {
+    if (int r = check_cfg(cfg)) return r;
+    if (!out) return fail(SACB_ERR_INVALID, "null out");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(SACB_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SACB_ERR_INVALID, "device %d out of range", cfg->device);
+    CU(cudaSetDevice(cfg->device));
+    sacb_engine* e = new sacb_engine();
+    e->cfg = *cfg;
+    e->rank = cfg->rank; e->world = 1;
+    compute_layout(*cfg, e->lay);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    e->num_sms = prop.multiProcessorCount;
+    CU(cudaFuncSetAttribute(sac_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sac_phase_kernel, kThreads, kSmemBytes));
+    if (occ < 1) { delete e; return fail(SACB_ERR_CUDA, "sac_phase_kernel does not fit on an SM"); }
+    if (occ > 2) occ = 2;
+    e->grid_coop = occ * e->num_sms;
+
+    const long long O = cfg->obs_dim, A = cfg->act_dim, H1 = cfg->hidden1, H2 = cfg->hidden2, B = cfg->batch_size;
+    e->ldx = (int)r4(O + A); e->lds = (int)r4(O); e->ldh = (int)r4(2 * A); e->lddpi = (int)r4(A);
+    e->tnH2 = (int)((H2 + kBN - 1) / kBN);
+    e->row_tiles = (int)((B + 7) / 8);
+    // carve the workspace
+    size_t off = 0;
+    auto take = [&](long long n) { size_t o = off; off += (size_t)r4(n); return o; };
+    struct Slot { float** p; size_t o; };
+    std::vector<Slot> slots;
+    auto want = [&](float*& p, long long n) { slots.push_back({&p, take(n)}); };
+    want(e->xs, B * e->ldx); want(e->xp, B * e->ldx); want(e->x2, B * e->ldx); want(e->s2buf, B * e->lds); want(e->rd, 2 * B);
+    want(e->ah1, B * H1); want(e->ah2, B * H2); want(e->heads, B * e->ldh); want(e->logp, 2 * B);
+    want(e->ch1, B * 2 * H1); want(e->ch2, B * 2 * H2); want(e->th1, B * 2 * H1); want(e->th2, B * 2 * H2);
+    want(e->qpart, 2LL * e->tnH2 * B); want(e->qtpart, 2LL * e->tnH2 * B); want(e->qbuf, 9 * B); want(e->qfw, 2 * B);
+    want(e->dh2, B * 2 * H2); want(e->dh1, B * 2 * H1); want(e->dpi, B * e->lddpi); want(e->ghead, B * e->ldh);
+    want(e->adh2, B * H2); want(e->adh1, B * H1);
+    want(e->lparts_q, 4LL * e->row_tiles); want(e->lparts_pi, 4LL * e->row_tiles); want(e->loss_scalar, 4);
+    want(e->ga, e->lay.actor_floats); want(e->gc, e->lay.critic_floats);
+    e->ws_floats = off;
+    CU(cudaMalloc(&e->ws, off * sizeof(float)));
+    CU(cudaMemset(e->ws, 0, off * sizeof(float)));
+    for (auto& s : slots) *s.p = e->ws + s.o;
+    CU(cudaMalloc(&e->idx_buf, (size_t)cfg->max_burst * B * sizeof(long long)));
+    CU(cudaMalloc(&e->eps_buf, (size_t)cfg->max_burst * 2 * B * A * sizeof(float)));
+    CU(cudaMalloc(&e->barrier, sizeof(unsigned long long)));
+    CU(cudaMemset(e->barrier, 0, sizeof(unsigned long long)));
+    CU(cudaEventCreateWithFlags(&e->stage_ev, cudaEventDisableTiming));
+    *out = e;
+    return 0;
+}
+
+int sacb_destroy(sacb_handle e) {
+    if (!e) return 0;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    cudaFree(e->ws); cudaFree(e->idx_buf); cudaFree(e->eps_buf); cudaFree(e->barrier);
+    cudaFree(e->d_jobs); cudaFree(e->d_phases);
+    if (e->stage) cudaFreeHost(e->stage);
+    if (e->stage_ev) cudaEventDestroy(e->stage_ev);
+    delete e;
+    return 0;
+}
+
+int sacb_bind_params(sacb_handle e, float* actor, float* critic, float* target) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    for (float* p : {actor, critic, target})
+        if (p && ((uintptr_t)p & 15)) return fail(SACB_ERR_INVALID, "parameter arenas must be 16-byte aligned");
+    e->pa = actor; e->pc = critic; e->pt = target;
+    e->dirty = true;
+    return 0;
+}
+
+int sacb_bind_adam(sacb_handle e, float* ma, float* va, int64_t step_a, float* mc, float* vc, int64_t step_c) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    for (float* p : {ma, va, mc, vc})
+        if (p && ((uintptr_t)p & 15)) return fail(SACB_ERR_INVALID, "Adam arenas must be 16-byte aligned");
+    e->ma = ma; e->va = va; e->mc = mc; e->vc = vc;
+    e->step_pi = step_a; e->step_q = step_c;
+    e->dirty = true;
+    return 0;
+}
+
+int sacb_get_adam_steps(sacb_handle e, int64_t* sa, int64_t* sc) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (sa) *sa = e->step_pi;
+    if (sc) *sc = e->step_q;
+    return 0;
+}
+
+int sacb_set_scalar(sacb_handle e, const char* name, double v) {
+    if (!e || !name) return fail(SACB_ERR_INVALID, "null argument");
+    sacb_config& c = e->cfg;
+    std::string n(name);
+    if (n == "alpha") c.alpha = (float)v;
+    else if (n == "gamma") c.gamma = (float)v;
+    else if (n == "polyak") c.polyak = (float)v;
+    else if (n == "reward_scale") c.reward_scale = (float)v;
+    else if (n == "lr_pi") c.lr_pi = v;
+    else if (n == "lr_q") c.lr_q = v;
+    else if (n == "beta1") c.beta1 = v;
+    else if (n == "beta2") c.beta2 = v;
+    else if (n == "adam_eps") c.adam_eps = v;
+    else return fail(SACB_ERR_INVALID, "unknown scalar '%s'", name);
+    return 0;
+}
+
+int sacb_bind_buffer(sacb_handle e, float* s, float* a, float* r, float* s2, uint8_t* d, int64_t cap) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (!s || !a || !r || !s2 || !d || cap < 1) return fail(SACB_ERR_INVALID, "bad buffer arrays");
+    e->bs = s; e->ba = a; e->br = r; e->bs2 = s2; e->bd = d; e->cap = cap;
+    if (e->ptr >= cap) e->ptr = 0;
+    if (e->size > cap) e->size = cap;
+    return 0;
+}
+
+int sacb_buffer_state(sacb_handle e, int64_t* ptr, int64_t* size, int64_t* cap) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (ptr) *ptr = e->ptr;
+    if (size) *size = e->size;
+    if (cap) *cap = e->cap;
+    return 0;
+}
+
+int sacb_set_buffer_state(sacb_handle e, int64_t ptr, int64_t size) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (ptr < 0 || size < 0 || size > e->cap || (e->cap && ptr >= e->cap)) return fail(SACB_ERR_INVALID, "ptr/size out of range");
+    e->ptr = ptr; e->size = size;
+    return 0;
+}
+
+int sacb_store(sacb_handle e, const float* obs, const float* act, const float* rew, const float* nobs, const uint8_t* done,
+               int64_t count, uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (int r = need(e->bs != nullptr, "replay buffer")) return r;
+    if (count < 0) return fail(SACB_ERR_INVALID, "negative count");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    const size_t O = e->cfg.obs_dim, A = e->cfg.act_dim;
+    const size_t row_bytes = (2 * O + A + 1) * sizeof(float) + 1;
+    const int64_t chunk_rows = 4096;
+    if (!e->stage) {
+        e->stage_bytes = (size_t)chunk_rows * row_bytes + 64;
+        CU(cudaMallocHost(&e->stage, e->stage_bytes));
+    }
+    int64_t done_rows = 0;
+    while (done_rows < count) {
+        // contiguous segment of the ring: [ptr, min(ptr+n, cap))
+        int64_t n = count - done_rows;
+        if (n > chunk_rows) n = chunk_rows;
+        if (n > e->cap - e->ptr) n = e->cap - e->ptr;
+        CU(cudaEventSynchronize(e->stage_ev));            // previous chunk's copies have drained the staging area
+        float* so = (float*)e->stage;
+        float* sa = so + n * O;
+        float* sr = sa + n * A;
+        float* sn = sr + n;
+        uint8_t* sd = (uint8_t*)(sn + n * O);
+        memcpy(so, obs + done_rows * O, n * O * sizeof(float));
+        memcpy(sa, act + done_rows * A, n * A * sizeof(float));
+        memcpy(sr, rew + done_rows, n * sizeof(float));
+        memcpy(sn, nobs + done_rows * O, n * O * sizeof(float));
+        for (int64_t i = 0; i < n; ++i) sd[i] = done[done_rows + i] ? 1 : 0;
+        CU(cudaMemcpyAsync(e->bs + e->ptr * O, so, n * O * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(e->ba + e->ptr * A, sa, n * A * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(e->br + e->ptr, sr, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(e->bs2 + e->ptr * O, sn, n * O * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(e->bd + e->ptr, sd, n, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(e->stage_ev, st));
+        e->ptr = (e->ptr + n) % e->cap;                                   // buffer/replay_buffer.py:42
+        e->size = e->size + n > e->cap ? e->cap : e->size + n;            // :43
+        done_rows += n;
+    }
+    return 0;
+}
+
+static int draw_indices(sacb_engine* e, long long* out, int n_sets, int B, cudaStream_t st) {
+    if (e->size < B) return fail(SACB_ERR_SAMPLE, "Sample larger than population or is negative (size=%lld, batch=%d)", e->size, B);
+    if (B > 16384) return fail(SACB_ERR_INVALID, "batch too large for the on-device sampler");
+    const unsigned long long seed = e->cfg.seed + 0x51ED270B9F5A3C1DULL * (unsigned long long)(e->rank + 1);
+    draw_indices_kernel<<<n_sets, 256, (size_t)B * sizeof(long long), st>>>(out, B, e->size, seed, e->rng_counter);
+    CU(cudaGetLastError());
+    e->launches++;
+    e->rng_counter += n_sets;
+    return 0;
+}
+
+static int draw_normals(sacb_engine* e, float* out, long long n, cudaStream_t st) {
+    const unsigned long long seed = e->cfg.seed + 0xA24BAED4963EE407ULL * (unsigned long long)(e->rank + 1);
+    const long long threads = (n + 3) / 4;
+    const int grid = (int)((threads + 255) / 256);
+    draw_normal_kernel<<<grid, 256, 0, st>>>(out, n, seed, e->rng_counter << 24);
+    CU(cudaGetLastError());
+    e->launches++;
+    e->rng_counter += 1;
+    return 0;
+}
+
+int sacb_sample(sacb_handle e, int32_t batch, const int64_t* idx_in, float* s, float* a, float* r, float* s2, float* d,
+                int64_t* idx_out, uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (int rr = need(e->bs != nullptr, "replay buffer")) return rr;
+    if (batch < 1) return fail(SACB_ERR_SAMPLE, "Sample larger than population or is negative");
+    if (e->size < batch) return fail(SACB_ERR_SAMPLE, "Sample larger than population or is negative (size=%lld, batch=%d)", e->size, batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    const long long* idx = (const long long*)idx_in;
+    long long* tmp = nullptr;
+    if (!idx) {
+        if ((long long)batch > (long long)e->cfg.max_burst * e->cfg.batch_size) {
+            CU(cudaMallocAsync(&tmp, (size_t)batch * sizeof(long long), st));
+            if (int rr = draw_indices(e, tmp, 1, batch, st)) return rr;
+            idx = tmp;
+        } else {
+            if (int rr = draw_indices(e, e->idx_buf, 1, batch, st)) return rr;
+            idx = e->idx_buf;
+        }
+    }
+    sample_gather_kernel<<<(batch + 7) / 8, 256, 0, st>>>(idx, batch, e->cfg.obs_dim, e->cfg.act_dim, e->bs, e->ba, e->br, e->bs2,
+                                                          e->bd, s, a, r, s2, d, (long long*)idx_out);
+    CU(cudaGetLastError());
+    e->launches++;
+    if (tmp) CU(cudaFreeAsync(tmp, st));
+    return 0;
+}
+
+// which: 1 = critic step (needs target + critic Adam), 2 = policy step (needs actor Adam), 3 = both
+static int check_train_bound(sacb_engine* e, int which) {
+    if (int r = need(e->pa && e->pc, "actor/critic parameters")) return r;
+    if (which & 1) {
+        if (int r = need(e->pt != nullptr, "target parameters")) return r;
+        if (int r = need(e->mc && e->vc, "critic Adam state")) return r;
+    }
+    if (which & 2)
+        if (int r = need(e->ma && e->va, "actor Adam state")) return r;
+    return 0;
+}
+
+static int allreduce(sacb_engine* e, float* buf, long long n, cudaStream_t st) {
+    NC(g_nccl.AllReduce(buf, buf, (size_t)n, kNcclFloat, kNcclSum, e->comm, st));
+    return 0;
+}
+
+int sacb_update(sacb_handle e, int32_t n_updates, const int64_t* idx_in, const float* eps_in, float* loss_q, float* loss_pi,
+                uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (int r = check_train_bound(e, 3)) return r;
+    if (int r = need(e->bs != nullptr, "replay buffer")) return r;
+    if (n_updates < 0 || n_updates > e->cfg.max_burst) return fail(SACB_ERR_INVALID, "n_updates %d exceeds max_burst %d", n_updates, e->cfg.max_burst);
+    if (n_updates == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    if (int r = upload_programs(e, st)) return r;
+    const int B = e->cfg.batch_size, A = e->cfg.act_dim;
+    if (e->size < B) return fail(SACB_ERR_SAMPLE, "Sample larger than population or is negative (size=%lld, batch=%d)", e->size, B);
+    const long long* idx = (const long long*)idx_in;
+    if (!idx) {
+        if (int r = draw_indices(e, e->idx_buf, n_updates, B, st)) return r;
+        idx = e->idx_buf;
+    }
+    const float* eps = eps_in;
+    if (!eps) {
+        if (int r = draw_normals(e, e->eps_buf, (long long)n_updates * 2 * B * A, st)) return r;
+        eps = e->eps_buf;
+    }
+    RunArgs ra;
+    fill_args(e, ra);
+    ra.idx = idx; ra.idx_stride = B;
+    ra.eps1 = eps; ra.eps2 = eps + (size_t)B * A; ra.eps_stride = 2LL * B * A;
+    ra.loss_q_out = loss_q; ra.loss_pi_out = loss_pi;
+    ra.fuse_polyak = 1; ra.pass_mask = 3;
+    if (e->world <= 1) {
+        if (int r = run_phases(e, ra, e->p_update.begin, e->p_update.end, 0, n_updates, st)) return r;
+    } else {
+        const bool sync_actor = !(e->cfg.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC);
+        for (int k = 0; k < n_updates; ++k) {
+            if (int r = run_phases(e, ra, e->p_update.begin, e->ph_crit_adam, k, k + 1, st)) return r;
+            if (int r = allreduce(e, e->gc, e->lay.critic_floats, st)) return r;         // mpi_avg_grads(critic), algorithm.py:138
+            if (sync_actor) {
+                if (int r = run_phases(e, ra, e->ph_crit_adam, e->ph_pi_adam, k, k + 1, st)) return r;
+                if (int r = allreduce(e, e->ga, e->lay.actor_floats, st)) return r;      // intent of algorithm.py:155
+                if (int r = run_phases(e, ra, e->ph_pi_adam, e->p_update.end, k, k + 1, st)) return r;
+            } else {
+                RunArgs rb = ra;
+                if (int r = run_phases(e, rb, e->ph_crit_adam, e->ph_pi_adam, k, k + 1, st)) return r;
+                rb.grad_div = 1.f;
+                if (int r = run_phases(e, rb, e->ph_pi_adam, e->p_update.end, k, k + 1, st)) return r;
+            }
+        }
+    }
+    e->step_pi += n_updates; e->step_q += n_updates;
+    return 0;
+}
+
+int sacb_load_batch(sacb_handle e, const float* s, const float* a, const float* r, const float* s2, const float* d, uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (!s || !a || !r || !s2 || !d) return fail(SACB_ERR_INVALID, "null batch array");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    const int B = e->cfg.batch_size;
+    load_batch_kernel<<<(B + 7) / 8, 256, 0, st>>>(s, a, r, s2, d, B, e->cfg.obs_dim, e->cfg.act_dim, e->xs, e->xp, e->x2, e->s2buf,
+                                                   e->rd, e->ldx, e->lds);
+    CU(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+static int eps_or_draw(sacb_engine* e, const float* eps_in, const float** eps_out, cudaStream_t st) {
+    if (eps_in) { *eps_out = eps_in; return 0; }
+    const long long n = (long long)e->cfg.batch_size * e->cfg.act_dim;
+    if (int r = draw_normals(e, e->eps_buf, n, st)) return r;
+    *eps_out = e->eps_buf;
+    return 0;
+}
+
+int sacb_update_critic(sacb_handle e, const float* eps_in, float* loss_q, uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (int r = check_train_bound(e, 1)) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    if (int r = upload_programs(e, st)) return r;
+    const float* eps = nullptr;
+    if (int r = eps_or_draw(e, eps_in, &eps, st)) return r;
+    RunArgs ra;
+    fill_args(e, ra);
+    ra.eps1 = eps; ra.eps2 = nullptr; ra.eps_stride = 0; ra.pass_mask = 1; ra.fuse_polyak = 0;
+    ra.loss_q_out = loss_q;
+    if (e->world <= 1) {
+        if (int r = run_phases(e, ra, e->ph_crit_begin, e->ph_crit_adam + 1, 0, 1, st)) return r;
+    } else {
+        if (int r = run_phases(e, ra, e->ph_crit_begin, e->ph_crit_adam, 0, 1, st)) return r;
+        if (int r = allreduce(e, e->gc, e->lay.critic_floats, st)) return r;
+        if (int r = run_phases(e, ra, e->ph_crit_adam, e->ph_crit_adam + 1, 0, 1, st)) return r;
+    }
+    e->step_q += 1;
+    return 0;
+}
+
+int sacb_update_policy(sacb_handle e, const float* eps_in, float* loss_pi, uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (int r = check_train_bound(e, 2)) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    if (int r = upload_programs(e, st)) return r;
+    const float* eps = nullptr;
+    if (int r = eps_or_draw(e, eps_in, &eps, st)) return r;
+    RunArgs ra;
+    fill_args(e, ra);
+    ra.eps1 = nullptr; ra.eps2 = eps; ra.eps_stride = 0; ra.pass_mask = 2; ra.fuse_polyak = 0;
+    ra.loss_pi_out = loss_pi;
+    const int adam = e->p_policy.end - 1;
+    const bool sync_actor = e->world > 1 && !(e->cfg.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC);
+    if (!sync_actor) {
+        ra.grad_div = 1.f;
+        if (int r = run_phases(e, ra, e->p_policy.begin, e->p_policy.end, 0, 1, st)) return r;
+    } else {
+        if (int r = run_phases(e, ra, e->p_policy.begin, adam, 0, 1, st)) return r;
+        if (int r = allreduce(e, e->ga, e->lay.actor_floats, st)) return r;
+        if (int r = run_phases(e, ra, adam, e->p_policy.end, 0, 1, st)) return r;
+    }
+    e->step_pi += 1;
+    return 0;
+}
+
+int sacb_update_targets(sacb_handle e, uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (int r = need(e->pc && e->pt, "critic/target parameters")) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    if (int r = upload_programs(e, st)) return r;
+    RunArgs ra;
+    fill_args(e, ra);
+    return run_phases(e, ra, e->p_targets.begin, e->p_targets.end, 0, 1, st);
+}
+
+int sacb_actor_forward(sacb_handle e, const float* x, int32_t n, const float* eps_in, int32_t deterministic, float* pi, float* logp,
+                       uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (int r = need(e->pa != nullptr, "actor parameters")) return r;
+    if (n < 0 || !x || !pi) return fail(SACB_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    if (int r = upload_programs(e, st)) return r;
+    const int B = e->cfg.batch_size, O = e->cfg.obs_dim, A = e->cfg.act_dim;
+    for (int r0 = 0; r0 < n; r0 += B) {
+        const int m = (n - r0) < B ? (n - r0) : B;
+        CU(cudaMemcpy2DAsync(e->s2buf, e->lds * sizeof(float), x + (size_t)r0 * O, O * sizeof(float), O * sizeof(float), m,
+                             cudaMemcpyDeviceToDevice, st));
+        const float* eps = nullptr;
+        if (!deterministic) {
+            if (eps_in) eps = eps_in + (size_t)r0 * A;
+            else {
+                if (int r = draw_normals(e, e->eps_buf, (long long)m * A, st)) return r;
+                eps = e->eps_buf;
+            }
+        }
+        RunArgs ra;
+        fill_args(e, ra);
+        ra.m_rows = m; ra.pass_mask = 1; ra.eps1 = eps; ra.eps2 = nullptr; ra.eps_stride = 0;
+        if (int r = run_phases(e, ra, e->p_actor_fwd.begin, e->p_actor_fwd.end, 0, 1, st)) return r;
+        CU(cudaMemcpy2DAsync(pi + (size_t)r0 * A, A * sizeof(float), e->x2 + O, e->ldx * sizeof(float), A * sizeof(float), m,
+                             cudaMemcpyDeviceToDevice, st));
+        if (logp) CU(cudaMemcpyAsync(logp + r0, e->logp, m * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+int sacb_critic_forward(sacb_handle e, int32_t which, const float* s, const float* a, int32_t n, float* q1, float* q2, uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (which != 0 && which != 1) return fail(SACB_ERR_INVALID, "which must be 0 (critic) or 1 (target)");
+    if (int r = need((which ? e->pt : e->pc) != nullptr, which ? "target parameters" : "critic parameters")) return r;
+    if (n < 0 || !s || !a || !q1 || !q2) return fail(SACB_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    if (int r = upload_programs(e, st)) return r;
+    const int B = e->cfg.batch_size, O = e->cfg.obs_dim, A = e->cfg.act_dim;
+    for (int r0 = 0; r0 < n; r0 += B) {
+        const int m = (n - r0) < B ? (n - r0) : B;
+        CU(cudaMemcpy2DAsync(e->xs, e->ldx * sizeof(float), s + (size_t)r0 * O, O * sizeof(float), O * sizeof(float), m,
+                             cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpy2DAsync(e->xs + O, e->ldx * sizeof(float), a + (size_t)r0 * A, A * sizeof(float), A * sizeof(float), m,
+                             cudaMemcpyDeviceToDevice, st));
+        RunArgs ra;
+        fill_args(e, ra);
+        ra.m_rows = m;
+        if (int r = run_phases(e, ra, e->p_critic_fwd[which].begin, e->p_critic_fwd[which].end, 0, 1, st)) return r;
+        CU(cudaMemcpyAsync(q1 + r0, e->qfw, m * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(q2 + r0, e->qfw + B, m * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+int sacb_comm_unique_id(const char* lib, uint8_t id_out[128]) {
+    if (int r = load_nccl(lib)) return r;
+    nccl_uid_t id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, id.internal, 128);
+    return 0;
+}
+
+int sacb_comm_init(sacb_handle e, const char* lib, const uint8_t id_in[128], int32_t rank, int32_t world) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (world < 1 || rank < 0 || rank >= world) return fail(SACB_ERR_INVALID, "bad rank/world");
+    if (int r = load_nccl(lib)) return r;
+    CU(cudaSetDevice(e->cfg.device));
+    nccl_uid_t id;
+    memcpy(id.internal, id_in, 128);
+    NC(g_nccl.CommInitRank(&e->comm, world, id, rank));
+    e->rank = rank; e->world = world;
+    return 0;
+}
+
+int sacb_sync_params(sacb_handle e, uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (e->world <= 1) return 0;                      // sync_params early return, sac/mpi.py:94-95
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    if (e->pa) NC(g_nccl.Broadcast(e->pa, e->pa, (size_t)e->lay.actor_floats, kNcclFloat, 0, e->comm, st));
+    if (e->pc) NC(g_nccl.Broadcast(e->pc, e->pc, (size_t)e->lay.critic_floats, kNcclFloat, 0, e->comm, st));
+    if (e->pt) NC(g_nccl.Broadcast(e->pt, e->pt, (size_t)e->lay.critic_floats, kNcclFloat, 0, e->comm, st));
+    return 0;
+}
+
+int sacb_debug_read(sacb_handle e, const char* name, float* dst, int64_t max_floats, int64_t* n_out) {
+    if (!e || !name || !dst) return fail(SACB_ERR_INVALID, "null argument");
+    const long long B = e->cfg.batch_size, A = e->cfg.act_dim, O = e->cfg.obs_dim;
+    std::string n(name);
+    const float* src = nullptr;
+    long long cnt = 0, rows = 0, cols = 0, ld = 0;
+    if (n == "q1") { src = e->qbuf; cnt = B; }
+    else if (n == "q2") { src = e->qbuf + B; cnt = B; }
+    else if (n == "q1_target") { src = e->qbuf + 2 * B; cnt = B; }
+    else if (n == "q2_target") { src = e->qbuf + 3 * B; cnt = B; }
+    else if (n == "backup") { src = e->qbuf + 4 * B; cnt = B; }
+    else if (n == "dq1") { src = e->qbuf + 5 * B; cnt = B; }
+    else if (n == "dq2") { src = e->qbuf + 6 * B; cnt = B; }
+    else if (n == "q1_pi") { src = e->qbuf + 7 * B; cnt = B; }
+    else if (n == "q2_pi") { src = e->qbuf + 8 * B; cnt = B; }
+    else if (n == "logp_next") { src = e->logp; cnt = B; }
+    else if (n == "logp_pi") { src = e->logp + B; cnt = B; }
+    else if (n == "a2") { src = e->x2 + O; rows = B; cols = A; ld = e->ldx; }
+    else if (n == "pi") { src = e->xp + O; rows = B; cols = A; ld = e->ldx; }
+    else if (n == "grad_actor") { src = e->ga; cnt = e->lay.actor_floats; }
+    else if (n == "grad_critic") { src = e->gc; cnt = e->lay.critic_floats; }
+    else if (n == "loss") { src = e->loss_scalar; cnt = 2; }
+    else if (n == "rewards") { src = e->rd; cnt = B; }
+    else if (n == "done") { src = e->rd + B; cnt = B; }
+    else return fail(SACB_ERR_INVALID, "unknown debug array '%s'", name);
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaDeviceSynchronize());
+    if (rows) {
+        if (rows * cols > max_floats) return fail(SACB_ERR_INVALID, "destination too small");
+        CU(cudaMemcpy2D(dst, cols * sizeof(float), src, ld * sizeof(float), cols * sizeof(float), rows, cudaMemcpyDeviceToHost));
+        if (n_out) *n_out = rows * cols;
+    } else {
+        if (cnt > max_floats) return fail(SACB_ERR_INVALID, "destination too small");
+        CU(cudaMemcpy(dst, src, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+        if (n_out) *n_out = cnt;
+    }
+    return 0;
+}
+
+int64_t sacb_launch_count(sacb_handle e) { return e ? e->launches : 0; }
+
+int sacb_set_mode(sacb_handle e, int32_t mode) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (mode != 0 && mode != 1) return fail(SACB_ERR_INVALID, "mode must be 0 or 1");
+    e->mode = mode;
+    return 0;
+}
+
+}  // extern "C"
