@@ -95,8 +95,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_rate(arrays, threads, n_updates, warmup):
-    """updates/s of the torch-CPU port of sac/algorithm.py:274-281 on the host (oracle = checker / baseline only)."""
+def cpu_port_rate(arrays, threads, n_updates, warmup, max_seconds):
+    """updates/s of the torch-CPU port of sac/algorithm.py:274-281 on the host (oracle = checker / baseline only).
+    Bounded: stops after `max_seconds` of timed work."""
     import torch
     from oracle.sac_numpy import HyperParams, init_params
     from oracle.sac_torch_cpu import HostReplay, TorchCpuSAC, time_cpu_updates
@@ -104,8 +105,22 @@ def cpu_port_rate(arrays, threads, n_updates, warmup):
     actor, critic = init_params(O, A, H, np.random.default_rng(0))
     sac = TorchCpuSAC(actor, critic, HyperParams(act_limit=1.0))
     replay = HostReplay(arrays["state"], arrays["actions"], arrays["rewards"], arrays["next_state"], arrays["done"])
-    dt = time_cpu_updates(replay, sac, B, n_updates, warmup, UPDATE_EVERY)
-    return n_updates / dt
+    dt, done = time_cpu_updates(replay, sac, B, n_updates, warmup, UPDATE_EVERY, max_seconds=max_seconds)
+    return done / dt, done
+
+
+def cpu_baseline(arrays, steps, warmup, budget_s):
+    """Best thread count among 1, 2 (the reference's own setting, main.py:130), 8, 16, 32 (<= host cores): the update is a
+    chain of tiny GEMMs, so more threads stop helping early and oversubscription hurts.  Short probes pick the thread
+    count, then the bounded sample runs at it."""
+    cores = os.cpu_count() or 1
+    cands = sorted({t for t in (1, 2, 8, 16, 32) if t <= cores})
+    probe = {}
+    for t in cands:
+        probe[t] = round(cpu_port_rate(arrays, t, 40, 5, budget_s / (4 * len(cands)))[0], 2)
+    best = max(probe, key=probe.get)
+    rate, done = cpu_port_rate(arrays, best, steps, warmup, budget_s / 2)
+    return rate, best, done, probe, cores
 
 
 def run_reference(args):
@@ -114,23 +129,15 @@ def run_reference(args):
         return
     import torch
     arrays = synth_buffer(0)
-    cores = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 3000))            # bounded sample: <= ~40 s of CPU work at ~100 updates/s
-    warm = max(3, min(args.warmup, 50))
-    best, best_thr, tried = 0.0, 1, {}
-    for thr in sorted({2, cores}):                   # 2 = the reference's own setting (main.py:130); all host cores
-        n = steps if thr == cores else max(50, steps // 4)
-        rate = cpu_port_rate(arrays, thr, n, warm)
-        tried[thr] = round(rate, 2)
-        if rate > best:
-            best, best_thr = rate, thr
-    sample = f"{steps} updates (bursts of {UPDATE_EVERY}) after {warm} warm-up, torch {torch.__version__} CPU, threads tried {tried}"
-    line = {"impl": "reference", "metric": METRIC, "value": round(best, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": round(1000.0 / best, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    rate, thr, done, probe, cores = cpu_baseline(arrays, max(1, args.steps), max(3, min(args.warmup, 50)), budget_s=60.0)
+    sample = (f"{done} updates (bursts of {UPDATE_EVERY}) timed at {thr} torch threads after warm-up, torch {torch.__version__} CPU; "
+              f"thread probe (updates/s) {probe}; host cpu_count={cores}")
+    line = {"impl": "reference", "metric": METRIC, "value": round(rate, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": max(3, min(args.warmup, 50)), "ms_per_step": round(1000.0 / rate, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "update_every": UPDATE_EVERY, "host_cpu_count": cores},
-            "cpu_baseline": {"value": round(best, 2), "unit": UNIT, "cores": best_thr, "kind": "port", "sample": sample},
-            "e2e": {"value": round(best, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {"value": round(rate, 2), "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
+            "e2e": {"value": round(rate, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -219,6 +226,7 @@ def run_gpu(args):
         return ms
 
     eng = sac._engine(actor, critic, B, target=target, pi_opt=pi_opt, q_opt=q_opt)
+    eng.set_mode(args.mode)
     run_updates(args.warmup, False)                                 # W untimed warm-up steps
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
@@ -270,19 +278,12 @@ def run_gpu(args):
                      "flops": {"achieved_tflops": round(FLOPS_PER_UPDATE * upd_per_launch / (k_ms * 1e-3) / 1e12, 3),
                                "note": "fp32 FFMA path; latency-bound dependency chain of ~20 phases per update"}},
     }
-    if world == 1:
-        cores = os.cpu_count() or 1
-        n_cpu = 400
-        tried = {}
-        for thr in sorted({2, cores}):
-            tried[thr] = round(cpu_port_rate(arrays, thr, n_cpu if thr == cores else 150, 20), 2)
-        best_thr = max(tried, key=tried.get)
-        line["cpu_baseline"] = {"value": tried[best_thr], "unit": UNIT, "cores": best_thr, "kind": "port",
-                                "sample": f"{n_cpu} updates after 20 warm-up on the same synthetic arrays; threads tried {tried}; "
-                                          f"host cpu_count={cores}"}
+    if world == 1 and not args.no_cpu:
+        rate, thr, done, probe, cores = cpu_baseline(arrays, 600, 20, budget_s=30.0)
+        line["cpu_baseline"] = {"value": round(rate, 2), "unit": UNIT, "cores": thr, "kind": "port",
+                                "sample": f"{done} updates at {thr} torch threads on the same synthetic arrays; thread probe "
+                                          f"(updates/s) {probe}; host cpu_count={cores}"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        pass
 
 
 def main():
@@ -291,6 +292,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", type=int, default=0, help="profiling only: 1 = one kernel launch per phase")
+    ap.add_argument("--no-cpu", action="store_true", help="profiling only: skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -52,8 +52,10 @@ typedef struct sacb_config {
     int32_t hidden1, hidden2;  /* MLP widths; the reference uses [256,256] (main.py:61) */
     int32_t batch_size;        /* B, rows per gradient update (main.py:153; BASELINE uses 256) */
     int32_t max_burst;         /* max updates per sacb_update call (reference update_every = 50, main.py:157) */
-    float alpha, gamma, polyak, reward_scale;        /* main.py:148-151 */
     float log_min_std, log_max_std, act_limit;       /* networks/linear.py:19-21 */
+    int32_t reserved0;
+    double alpha, gamma, polyak, reward_scale;       /* main.py:148-151; python floats in the reference, so doubles here:
+                                                        (1 - polyak) is formed in double before it is rounded to f32 */
     double lr_pi, lr_q, beta1, beta2, adam_eps;      /* torch.optim.Adam, main.py:93-95 */
     uint32_t flags;            /* SACB_FLAG_* */
     uint64_t seed;             /* Philox seed for on-device index / noise draws */
@@ -155,6 +157,11 @@ int sacb_sync_params(sacb_handle h, uintptr_t stream);
  * "q2_target","a2","logp_next","pi","logp_pi","q1_pi","q2_pi","grad_actor","grad_critic","loss_q_parts", ...
  * Returns the number of floats written via *n_out. */
 int sacb_debug_read(sacb_handle h, const char* name, float* dst_host, int64_t max_floats, int64_t* n_out);
+/* Test / debug: run n_updates like sacb_update with device-drawn inputs while every CTA stamps %globaltimer after the
+ * work and after the grid barrier of every phase.  stamps_host receives [n_updates][n_phases][n_ctas][2] uint64 ns;
+ * n_phases / n_ctas are returned.  Synchronous. */
+int sacb_debug_profile(sacb_handle h, int32_t n_updates, uint64_t* stamps_host, int64_t max_words, int32_t* n_phases,
+                       int32_t* n_ctas, uintptr_t stream);
 /* Number of kernel launches the engine has enqueued so far (bench `gpu_launches`). */
 int64_t sacb_launch_count(sacb_handle h);
 /* Execution mode: 0 = persistent cooperative kernel (default), 1 = one launch per phase (debug / profiling). */

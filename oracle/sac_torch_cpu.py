@@ -159,11 +159,16 @@ class HostReplay:
                     done=torch.FloatTensor(self.done[idx]))
 
 
-def time_cpu_updates(replay: HostReplay, sac: TorchCpuSAC, batch_size, n_updates, warmup, update_every=50):
-    """Time the burst loop sac/algorithm.py:273-281 (incl. the two per-update loss readbacks, :280-281)."""
+def time_cpu_updates(replay: HostReplay, sac: TorchCpuSAC, batch_size, n_updates, warmup, update_every=50,
+                     max_seconds=None):
+    """Time the burst loop sac/algorithm.py:273-281 (incl. the two per-update loss readbacks, :280-281).
+    Returns (seconds, updates_done); stops early once `max_seconds` of timed work have elapsed."""
     import time
+    t_w = time.perf_counter()
     for _ in range(warmup):
         lq, lp = sac.update_fast(replay.sample(batch_size))
+        if max_seconds is not None and time.perf_counter() - t_w > max_seconds:
+            break
     t0 = time.perf_counter()
     done = 0
     while done < n_updates:
@@ -171,4 +176,6 @@ def time_cpu_updates(replay: HostReplay, sac: TorchCpuSAC, batch_size, n_updates
             lq, lp = sac.update_fast(replay.sample(batch_size))
             lp.cpu().detach().numpy(); lq.cpu().detach().numpy()
             done += 1
-    return time.perf_counter() - t0
+            if max_seconds is not None and time.perf_counter() - t0 > max_seconds:
+                return time.perf_counter() - t0, done
+    return time.perf_counter() - t0, done

@@ -269,8 +269,20 @@ def test_device_sampler_without_replacement_and_uniform():
         counts[r] += 1
     expect = 200 * B / n
     assert np.all(np.abs(counts - expect) < 6 * np.sqrt(expect * (1 - B / n)) + 1)   # uniform inclusion probability
-    full = buf.sample(n)                                          # B == size: a permutation
+    full = buf.sample(n)                                          # B == size: a permutation (dense regime, Fisher-Yates)
     assert np.array_equal(np.sort(full.rewards.cpu().numpy()), np.arange(n))
+    # sparse regime (size >= 4B): rejection sampler
+    n2 = 5000
+    buf2 = ReplayBuffer(n2, 2, 1, seed=4)
+    obs2 = np.arange(n2, dtype=np.float32)[:, None].repeat(2, 1)
+    buf2.store_many(obs2, np.zeros((n2, 1), np.float32), np.arange(n2, dtype=np.float32), obs2, np.zeros(n2, bool))
+    counts2 = np.zeros(n2)
+    for _ in range(400):
+        r = buf2.sample(B).rewards.cpu().numpy().astype(int)
+        assert len(np.unique(r)) == B
+        counts2[r] += 1
+    e2 = 400 * B / n2
+    assert np.all(np.abs(counts2 - e2) < 6 * np.sqrt(e2) + 1) and counts2.min() > 0
 
 
 def _c1_setup(N=1_000_000, seed=0):

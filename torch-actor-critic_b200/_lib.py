@@ -16,8 +16,8 @@ class SacbConfig(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32),
         ("hidden1", C.c_int32), ("hidden2", C.c_int32), ("batch_size", C.c_int32), ("max_burst", C.c_int32),
-        ("alpha", C.c_float), ("gamma", C.c_float), ("polyak", C.c_float), ("reward_scale", C.c_float),
-        ("log_min_std", C.c_float), ("log_max_std", C.c_float), ("act_limit", C.c_float),
+        ("log_min_std", C.c_float), ("log_max_std", C.c_float), ("act_limit", C.c_float), ("reserved0", C.c_int32),
+        ("alpha", C.c_double), ("gamma", C.c_double), ("polyak", C.c_double), ("reward_scale", C.c_double),
         ("lr_pi", C.c_double), ("lr_q", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
         ("adam_eps", C.c_double), ("flags", C.c_uint32), ("seed", C.c_uint64), ("rank", C.c_int32), ("world", C.c_int32),
     ]
@@ -67,6 +67,7 @@ _PROTOS = {
     "sacb_comm_init": (C.c_int, [_P, C.c_char_p, _P, _I32, _I32]),
     "sacb_sync_params": (C.c_int, [_P, _U]),
     "sacb_debug_read": (C.c_int, [_P, C.c_char_p, _P, _I64, C.POINTER(_I64)]),
+    "sacb_debug_profile": (C.c_int, [_P, _I32, _P, _I64, C.POINTER(_I32), C.POINTER(_I32), _U]),
     "sacb_launch_count": (_I64, [_P]),
     "sacb_set_mode": (C.c_int, [_P, _I32]),
 }

@@ -108,6 +108,8 @@ struct sacb_engine {
     float *xs, *xp, *x2, *s2buf, *rd, *ah1, *ah2, *heads, *logp, *ch1, *ch2, *th1, *th2, *qpart, *qtpart, *qbuf, *qfw,
         *dh2, *dh1, *dpi, *ghead, *adh2, *adh1, *lparts_q, *lparts_pi, *loss_scalar, *ga, *gc;
     long long* idx_buf = nullptr;
+    int* perm_buf = nullptr;
+    size_t perm_cap = 0;
     float* eps_buf = nullptr;
     unsigned long long* barrier = nullptr;
     unsigned long long rng_counter = 0;
@@ -177,6 +179,7 @@ struct Builder {
     }
     void add(Job j) {
         Phase& p = phases[cur];
+        if (p.job_count >= kMaxJobsPerPhase) { fprintf(stderr, "sacb: too many jobs in a phase\n"); abort(); }
         j.tile_begin = p.ntiles;
         p.ntiles += j.ntiles;
         p.job_count += 1;
@@ -416,24 +419,43 @@ static int upload_programs(sacb_engine* e, cudaStream_t st) {
 // small standalone kernels: RNG draws, dense batch load, sample gather
 // ------------------------------------------------------------------------------------------------------------
 // Duplicate-free uniform indices (random.sample(range(size), B), buffer/replay_buffer.py:46).  One CTA per update.
-// Every position draws from its own Philox subsequence; a position that collides with an EARLIER position redraws
-// (next counter of its subsequence) until the batch is duplicate free.  The procedure only compares values for
-// equality, so the result is uniform over ordered duplicate-free B-tuples.
+// Sparse regime (size >= 4B): every position draws from its own Philox subsequence; a position that collides with an
+// EARLIER position redraws (next counter of its subsequence) until the batch is duplicate free (each round succeeds
+// with probability >= 3/4 per position).  The procedure only compares values for equality, so the result is uniform
+// over ordered duplicate-free B-tuples.
+// Dense regime (size < 4B, e.g. the first bursts after update_after): exact partial Fisher-Yates over an explicit
+// permutation of range(size) in global scratch (parallel init, B sequential swaps by one thread).
 __global__ void __launch_bounds__(256) draw_indices_kernel(long long* __restrict__ out, int B, long long size,
-                                                           unsigned long long seed, unsigned long long counter0) {
+                                                           unsigned long long seed, unsigned long long counter0,
+                                                           int* __restrict__ perm_scratch) {
     extern __shared__ long long cand[];
     __shared__ int any_dup;
     const unsigned long long u = counter0 + blockIdx.x;
-    auto draw = [&](int i, int round) -> long long {
+    auto draw_below = [&](int i, int round, unsigned long long bound) -> long long {
         curandStatePhilox4_32_10_t st;
         curand_init(seed, (u << 20) + (unsigned long long)i, (unsigned long long)round, &st);
         uint4 r = curand4(&st);
         unsigned long long x = ((unsigned long long)r.x << 32) | r.y;
-        return (long long)__umul64hi(x, (unsigned long long)size);
+        return (long long)__umul64hi(x, bound);
     };
-    for (int i = threadIdx.x; i < B; i += blockDim.x) cand[i] = draw(i, 0);
+    if (size < 4LL * B) {
+        int* perm = perm_scratch + (size_t)blockIdx.x * 4 * B;
+        const int n = (int)size;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < B; ++i) {
+                int j = i + (int)draw_below(i, 0, (unsigned long long)(n - i));
+                int a = perm[i], b = perm[j];
+                perm[i] = b; perm[j] = a;
+                out[(size_t)blockIdx.x * B + i] = b;
+            }
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < B; i += blockDim.x) cand[i] = draw_below(i, 0, (unsigned long long)size);
     __syncthreads();
-    for (int round = 1; round < 64; ++round) {
+    for (int round = 1; round < 256; ++round) {
         if (threadIdx.x == 0) any_dup = 0;
         __syncthreads();
         long long redraw_mask = 0;       // up to 64 positions per thread (B <= 16384)
@@ -448,7 +470,7 @@ __global__ void __launch_bounds__(256) draw_indices_kernel(long long* __restrict
         if (!any_dup) break;
         q = 0;
         for (int i = threadIdx.x; i < B; i += blockDim.x, ++q)
-            if (redraw_mask & (1LL << q)) cand[i] = draw(i, round);
+            if (redraw_mask & (1LL << q)) cand[i] = draw_below(i, round, (unsigned long long)size);
         __syncthreads();
     }
     for (int i = threadIdx.x; i < B; i += blockDim.x) out[(size_t)blockIdx.x * B + i] = cand[i];
@@ -502,7 +524,8 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
     ra.jobs = e->d_jobs; ra.phases = e->d_phases;
     ra.barrier = e->barrier;
     ra.buf_state = e->bs; ra.buf_actions = e->ba; ra.buf_rewards = e->br; ra.buf_next_state = e->bs2; ra.buf_done = e->bd;
-    ra.alpha = c.alpha; ra.gamma = c.gamma; ra.polyak = c.polyak; ra.reward_scale = c.reward_scale;
+    ra.alpha = (float)c.alpha; ra.gamma = (float)c.gamma; ra.polyak = (float)c.polyak; ra.reward_scale = (float)c.reward_scale;
+    ra.polyak_c = (float)(1.0 - c.polyak);          // `(1 - polyak) * src` with a python-float polyak (sac/algorithm.py:81)
     ra.log_min_std = c.log_min_std; ra.log_max_std = c.log_max_std; ra.act_limit = c.act_limit;
     ra.lr_pi = c.lr_pi; ra.lr_q = c.lr_q; ra.beta1 = c.beta1; ra.beta2 = c.beta2; ra.adam_eps = c.adam_eps;
     ra.step_pi = e->step_pi; ra.step_q = e->step_q;
@@ -570,6 +593,7 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     CU(cudaGetDeviceProperties(&prop, cfg->device));
     e->num_sms = prop.multiProcessorCount;
     CU(cudaFuncSetAttribute(sac_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CU(cudaFuncSetAttribute(draw_indices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * (int)sizeof(long long)));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sac_phase_kernel, kThreads, kSmemBytes));
     if (occ < 1) { delete e; return fail(SACB_ERR_CUDA, "sac_phase_kernel does not fit on an SM"); }
@@ -599,6 +623,8 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     CU(cudaMemset(e->ws, 0, off * sizeof(float)));
     for (auto& s : slots) *s.p = e->ws + s.o;
     CU(cudaMalloc(&e->idx_buf, (size_t)cfg->max_burst * B * sizeof(long long)));
+    e->perm_cap = (size_t)cfg->max_burst * 4 * B;
+    CU(cudaMalloc(&e->perm_buf, e->perm_cap * sizeof(int)));
     CU(cudaMalloc(&e->eps_buf, (size_t)cfg->max_burst * 2 * B * A * sizeof(float)));
     CU(cudaMalloc(&e->barrier, sizeof(unsigned long long)));
     CU(cudaMemset(e->barrier, 0, sizeof(unsigned long long)));
@@ -612,7 +638,7 @@ int sacb_destroy(sacb_handle e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    cudaFree(e->ws); cudaFree(e->idx_buf); cudaFree(e->eps_buf); cudaFree(e->barrier);
+    cudaFree(e->ws); cudaFree(e->idx_buf); cudaFree(e->perm_buf); cudaFree(e->eps_buf); cudaFree(e->barrier);
     cudaFree(e->d_jobs); cudaFree(e->d_phases);
     if (e->stage) cudaFreeHost(e->stage);
     if (e->stage_ev) cudaEventDestroy(e->stage_ev);
@@ -650,10 +676,10 @@ int sacb_set_scalar(sacb_handle e, const char* name, double v) {
     if (!e || !name) return fail(SACB_ERR_INVALID, "null argument");
     sacb_config& c = e->cfg;
     std::string n(name);
-    if (n == "alpha") c.alpha = (float)v;
-    else if (n == "gamma") c.gamma = (float)v;
-    else if (n == "polyak") c.polyak = (float)v;
-    else if (n == "reward_scale") c.reward_scale = (float)v;
+    if (n == "alpha") c.alpha = v;
+    else if (n == "gamma") c.gamma = v;
+    else if (n == "polyak") c.polyak = v;
+    else if (n == "reward_scale") c.reward_scale = v;
     else if (n == "lr_pi") c.lr_pi = v;
     else if (n == "lr_q") c.lr_q = v;
     else if (n == "beta1") c.beta1 = v;
@@ -735,8 +761,15 @@ static int draw_indices(sacb_engine* e, long long* out, int n_sets, int B, cudaS
     if (e->size < B) return fail(SACB_ERR_SAMPLE, "Sample larger than population or is negative (size=%lld, batch=%d)", e->size, B);
     if (B > 16384) return fail(SACB_ERR_INVALID, "batch too large for the on-device sampler");
     const unsigned long long seed = e->cfg.seed + 0x51ED270B9F5A3C1DULL * (unsigned long long)(e->rank + 1);
-    draw_indices_kernel<<<n_sets, 256, (size_t)B * sizeof(long long), st>>>(out, B, e->size, seed, e->rng_counter);
+    int* perm = e->perm_buf;
+    int* tmp = nullptr;
+    if (e->size < 4LL * B && (size_t)n_sets * 4 * B > e->perm_cap) {       // dense regime with an oversize batch
+        CU(cudaMallocAsync(&tmp, (size_t)n_sets * 4 * B * sizeof(int), st));
+        perm = tmp;
+    }
+    draw_indices_kernel<<<n_sets, 256, (size_t)B * sizeof(long long), st>>>(out, B, e->size, seed, e->rng_counter, perm);
     CU(cudaGetLastError());
+    if (tmp) CU(cudaFreeAsync(tmp, st));
     e->launches++;
     e->rng_counter += n_sets;
     return 0;
@@ -1054,6 +1087,44 @@ int sacb_debug_read(sacb_handle e, const char* name, float* dst, int64_t max_flo
         CU(cudaMemcpy(dst, src, cnt * sizeof(float), cudaMemcpyDeviceToHost));
         if (n_out) *n_out = cnt;
     }
+    return 0;
+}
+
+int sacb_debug_profile(sacb_handle e, int32_t n_updates, uint64_t* out, int64_t max_words, int32_t* n_phases, int32_t* n_ctas,
+                       uintptr_t stream) {
+    if (!e || !out) return fail(SACB_ERR_INVALID, "null argument");
+    if (int r = check_train_bound(e, 3)) return r;
+    if (int r = need(e->bs != nullptr, "replay buffer")) return r;
+    if (n_updates < 1 || n_updates > e->cfg.max_burst) return fail(SACB_ERR_INVALID, "bad n_updates");
+    if (e->world > 1) return fail(SACB_ERR_INVALID, "profile is single-GPU only");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(e->cfg.device));
+    if (int r = upload_programs(e, st)) return r;
+    const int np = e->p_update.end - e->p_update.begin;
+    const long long words = (long long)n_updates * np * e->grid_coop * 2;
+    if (words > max_words) return fail(SACB_ERR_INVALID, "stamp buffer too small: need %lld words", words);
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, words * sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, words * sizeof(unsigned long long)));
+    const int B = e->cfg.batch_size, A = e->cfg.act_dim;
+    if (int r = draw_indices(e, e->idx_buf, n_updates, B, st)) return r;
+    if (int r = draw_normals(e, e->eps_buf, (long long)n_updates * 2 * B * A, st)) return r;
+    RunArgs ra;
+    fill_args(e, ra);
+    ra.idx = e->idx_buf; ra.idx_stride = B;
+    ra.eps1 = e->eps_buf; ra.eps2 = e->eps_buf + (size_t)B * A; ra.eps_stride = 2LL * B * A;
+    ra.fuse_polyak = 1; ra.pass_mask = 3; ra.prof = d;
+    const int saved_mode = e->mode;
+    e->mode = 0;
+    int rc = run_phases(e, ra, e->p_update.begin, e->p_update.end, 0, n_updates, st);
+    e->mode = saved_mode;
+    if (rc) { cudaFree(d); return rc; }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(out, d, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaFree(d));
+    e->step_pi += n_updates; e->step_q += n_updates;
+    if (n_phases) *n_phases = np;
+    if (n_ctas) *n_ctas = e->grid_coop;
     return 0;
 }
 

@@ -315,6 +315,15 @@ class Engine:
             out = out.reshape(self.batch_size, self.act_dim)
         return out
 
+    def profile_phases(self, n_updates):
+        """[n_updates, n_phases, n_ctas, 2] globaltimer stamps (ns): after each phase's work / after its grid barrier."""
+        cap = int(n_updates) * 64 * 1024 * 2
+        buf = np.zeros(cap, np.uint64)
+        nph, ncta = C.c_int32(), C.c_int32()
+        check(self._lib.sacb_debug_profile(self._h, int(n_updates), buf.ctypes.data, cap, C.byref(nph), C.byref(ncta), self._stream()))
+        n = int(n_updates) * nph.value * ncta.value * 2
+        return buf[:n].reshape(int(n_updates), nph.value, ncta.value, 2)
+
     def launch_count(self):
         return int(self._lib.sacb_launch_count(self._h))
 
