@@ -321,12 +321,13 @@ def test_full_size_c1_properties():
     assert torch.equal(pt, pt0 * pk + pcf * pc)
     # first Adam step moves every parameter with a non-zero gradient by lr (bias-corrected m/sqrt(v) = sign(g))
     gc = torch.from_numpy(eng.debug_read("grad_critic")).cuda()
-    nz = gc.abs() > 1e-12
-    assert torch.allclose((pc - pc0)[nz].abs(), torch.full_like(pc[nz], 3e-4), rtol=1e-3)
+    nz = gc.abs() > 1e-4          # |g| >> adam eps (1e-8): the step is lr * g/(|g| + eps*sqrt(bc2)) ~= lr
+    assert nz.float().mean() > 0.3
+    assert torch.allclose((pc - pc0)[nz].abs(), torch.full_like(pc[nz], 3e-4), rtol=2e-3, atol=2e-8)
     assert torch.equal((pc - pc0)[nz].sign(), -gc[nz].sign())
     ga = torch.from_numpy(eng.debug_read("grad_actor")).cuda()
-    nza = ga.abs() > 1e-12
-    assert torch.allclose((pa - pa0)[nza].abs(), torch.full_like(pa[nza], 3e-4), rtol=1e-3)
+    nza = ga.abs() > 1e-4
+    assert torch.allclose((pa - pa0)[nza].abs(), torch.full_like(pa[nza], 3e-4), rtol=2e-3, atol=2e-8)
     # a 50-update burst with device-drawn indices and noise: finite, and deterministic for a fixed seed
     lq1, lp1 = eng.update(50)
     eng2, pa2, pc2, pt2 = _c1_setup()

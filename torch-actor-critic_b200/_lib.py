@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsacb200.so")
+LIB_PATH = os.environ.get("SACB200_LIB") or os.path.join(_HERE, "libsacb200.so")   # override: investigation builds
 
 SACB_OK, SACB_ERR_INVALID, SACB_ERR_CUDA, SACB_ERR_STATE, SACB_ERR_SAMPLE, SACB_ERR_NCCL = 0, -1, -2, -3, -4, -5
 FLAG_CANONICAL_LOGPROB, FLAG_PI_FROM_STATES, FLAG_NO_ACTOR_GRAD_SYNC = 1, 2, 4

@@ -1109,6 +1109,9 @@ int sacb_debug_profile(sacb_handle e, int32_t n_updates, uint64_t* out, int64_t 
     const int B = e->cfg.batch_size, A = e->cfg.act_dim;
     if (int r = draw_indices(e, e->idx_buf, n_updates, B, st)) return r;
     if (int r = draw_normals(e, e->eps_buf, (long long)n_updates * 2 * B * A, st)) return r;
+#ifdef SACB_TRACE
+    { int z = 0; cudaMemcpyToSymbol(g_trace_n, &z, sizeof(int)); }
+#endif
     RunArgs ra;
     fill_args(e, ra);
     ra.idx = e->idx_buf; ra.idx_stride = B;
@@ -1120,6 +1123,17 @@ int sacb_debug_profile(sacb_handle e, int32_t n_updates, uint64_t* out, int64_t 
     e->mode = saved_mode;
     if (rc) { cudaFree(d); return rc; }
     CU(cudaStreamSynchronize(st));
+#ifdef SACB_TRACE
+    {
+        static unsigned long long h[1 << 16];
+        int n = 0;
+        cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(int));
+        cudaMemcpyFromSymbol(h, g_trace, sizeof(h));
+        fprintf(stderr, "TRACE %d events (id, dcycles)\n", n);
+        for (int i = 1; i < n; ++i)
+            fprintf(stderr, "%llu %lld\n", h[2 * i], (long long)(h[2 * i + 1] - h[2 * i - 1]));
+    }
+#endif
     CU(cudaMemcpy(out, d, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     CU(cudaFree(d));
     e->step_pi += n_updates; e->step_q += n_updates;
