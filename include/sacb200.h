@@ -164,6 +164,9 @@ int sacb_debug_profile(sacb_handle h, int32_t n_updates, uint64_t* stamps_host, 
                        int32_t* n_ctas, uintptr_t stream);
 /* Number of kernel launches the engine has enqueued so far (bench `gpu_launches`). */
 int64_t sacb_launch_count(sacb_handle h);
+/* GEMM arithmetic: 1 (default) = tensor cores with 3xTF32 error compensation (fp32-level accuracy: every product is
+ * a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation), 0 = plain fp32 FFMA. */
+int sacb_set_precision(sacb_handle h, int32_t tf32x3);
 /* Execution mode: 0 = persistent cooperative kernel (default), 1 = one launch per phase (debug / profiling). */
 int sacb_set_mode(sacb_handle h, int32_t mode);
 

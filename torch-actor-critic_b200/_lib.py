@@ -70,6 +70,7 @@ _PROTOS = {
     "sacb_debug_profile": (C.c_int, [_P, _I32, _P, _I64, C.POINTER(_I32), C.POINTER(_I32), _U]),
     "sacb_launch_count": (_I64, [_P]),
     "sacb_set_mode": (C.c_int, [_P, _I32]),
+    "sacb_set_precision": (C.c_int, [_P, _I32]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 

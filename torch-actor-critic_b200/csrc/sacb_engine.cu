@@ -93,6 +93,7 @@ struct sacb_engine {
     sacb_layout_info lay{};
     int num_sms = 0, grid_coop = 0;
     int mode = 0;
+    int tf32x3 = 1;                 // GEMM precision: 1 = tensor cores with 3xTF32 compensation, 0 = fp32 FFMA
     long long launches = 0;
     // bound arenas
     float *pa = nullptr, *pc = nullptr, *pt = nullptr;
@@ -157,7 +158,7 @@ static int check_cfg(const sacb_config* c) {
     if (c->struct_size != sizeof(sacb_config)) return fail(SACB_ERR_INVALID, "sacb_config size mismatch (ABI): got %u want %zu", c->struct_size, sizeof(sacb_config));
     if (c->obs_dim < 1 || c->act_dim < 1 || c->hidden1 < 1 || c->hidden2 < 1) return fail(SACB_ERR_INVALID, "dims must be positive");
     if (c->batch_size < 1 || c->batch_size > 65536) return fail(SACB_ERR_INVALID, "batch_size out of range");
-    if (c->max_burst < 1) return fail(SACB_ERR_INVALID, "max_burst must be >= 1");
+    if (c->max_burst < 1 || c->max_burst > kMaxBurst) return fail(SACB_ERR_INVALID, "max_burst must be in [1, %d]", kMaxBurst);
     if (c->flags & SACB_FLAG_PI_FROM_STATES) return fail(SACB_ERR_INVALID, "SACB_FLAG_PI_FROM_STATES is not implemented");
     return 0;
 }
@@ -179,7 +180,6 @@ struct Builder {
     }
     void add(Job j) {
         Phase& p = phases[cur];
-        if (p.job_count >= kMaxJobsPerPhase) { fprintf(stderr, "sacb: too many jobs in a phase\n"); abort(); }
         j.tile_begin = p.ntiles;
         p.ntiles += j.ntiles;
         p.job_count += 1;
@@ -196,7 +196,10 @@ struct Builder {
         j.M = M; j.N = N; j.K = K; j.nz = nz; j.rows_dynamic = dyn;
         j.a_vec = al16(A) && (lda % 4 == 0) && (sA % 4 == 0);
         j.b_vec = al16(B) && (ldb % 4 == 0) && (sB % 4 == 0);
-        j.ntiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN) * nz;
+        j.tn = (N + kBN - 1) / kBN;
+        j.tpz = ((M + kBM - 1) / kBM) * j.tn;
+        j.ntiles = j.tpz * nz;
+        if (nz > 2) { fprintf(stderr, "sacb: nz > 2 unsupported\n"); abort(); }
         return j;
     }
     Job colsum(const float* X, int ldx, long long sX, const float* w, long long sW, float* out, long long sOut, int M, int N, int nz) {
@@ -246,12 +249,17 @@ static void build_programs(sacb_engine* e) {
 
     // ---------------- full update: sample/gather -> update_critic -> update_policy -> update_targets ----------------
     e->p_update.begin = (int)e->phases.size();
-    {   // P0 gather (ReplayBuffer.sample, buffer/replay_buffer.py:45-54)
-        b.phase();
+    auto gather = [&](int k_offset) {
         Job j = Builder::zero();
         j.type = J_GATHER; j.M = B; j.C = e->xs; j.out0 = e->xp; j.out1 = e->x2; j.ldc = ldx; j.out2 = e->s2buf; j.ldb = lds;
-        j.out3 = e->rd; j.ntiles = (B + 7) / 8;
-        b.add(j);
+        j.out3 = e->rd; j.ntiles = (B + 7) / 8; j.k_offset = k_offset;
+        return j; };
+    {   // P0 gather (ReplayBuffer.sample, buffer/replay_buffer.py:45-54).  Runs for the first update of a launch only:
+        // every later batch is prefetched by the last phase of the previous update (the indices of the whole burst
+        // are known up front), so the HBM latency of the random-row gather is off the critical path.
+        int p0 = b.phase();
+        e->phases[p0].pad = 1;
+        b.add(gather(0));
     }
     e->ph_crit_begin = (int)e->phases.size();
     b.phase(); b.add(actor_l0(0)); b.add(critic_l0(PC, e->xs, e->ch1, 0));                 // P1
@@ -349,6 +357,7 @@ static void build_programs(sacb_engine* e) {
     };
     e->ph_pi_begin = (int)e->phases.size();
     e->ph_pi_adam = policy_tail();
+    b.add(gather(1));                                      // prefetch the next update's batch (staging tiles are idle here)
     e->p_update.end = (int)e->phases.size();
 
     // ---------------- standalone update_policy (actor trunk recomputed) ----------------
@@ -527,8 +536,18 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
     ra.alpha = (float)c.alpha; ra.gamma = (float)c.gamma; ra.polyak = (float)c.polyak; ra.reward_scale = (float)c.reward_scale;
     ra.polyak_c = (float)(1.0 - c.polyak);          // `(1 - polyak) * src` with a python-float polyak (sac/algorithm.py:81)
     ra.log_min_std = c.log_min_std; ra.log_max_std = c.log_max_std; ra.act_limit = c.act_limit;
-    ra.lr_pi = c.lr_pi; ra.lr_q = c.lr_q; ra.beta1 = c.beta1; ra.beta2 = c.beta2; ra.adam_eps = c.adam_eps;
-    ra.step_pi = e->step_pi; ra.step_q = e->step_q;
+    ra.adam_w1 = (float)(1.0 - c.beta1); ra.adam_b2 = (float)c.beta2; ra.adam_w2 = (float)(1.0 - c.beta2);
+    ra.adam_eps = (float)c.adam_eps;
+    // torch._single_tensor_adam forms these in python doubles per step: bias_correction{1,2} = 1 - beta^t,
+    // step_size = lr / bc1, bc2_sqrt = bc2 ** 0.5; the kernels consume them as float32 scalars like torch does.
+    for (int k = 0; k < kMaxBurst; ++k) {
+        const double ta = (double)(e->step_pi + k + 1), tq = (double)(e->step_q + k + 1);
+        ra.adam_coef[k][0] = (float)(-(c.lr_pi / (1.0 - std::pow(c.beta1, ta))));
+        ra.adam_coef[k][1] = (float)std::sqrt(1.0 - std::pow(c.beta2, ta));
+        ra.adam_coef[k][2] = (float)(-(c.lr_q / (1.0 - std::pow(c.beta1, tq))));
+        ra.adam_coef[k][3] = (float)std::sqrt(1.0 - std::pow(c.beta2, tq));
+    }
+    ra.tf32x3 = e->tf32x3;
     ra.grad_div = (float)e->world;
     ra.flags = c.flags;
     ra.O = c.obs_dim; ra.A = c.act_dim; ra.H1 = c.hidden1; ra.H2 = c.hidden2; ra.B = c.batch_size;
@@ -538,6 +557,10 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
 // Run phases [pb, pe) for updates [kb, ke).  Cooperative persistent launch unless mode==1 or a single phase.
 static int run_phases(sacb_engine* e, RunArgs ra, int pb, int pe, int kb, int ke, cudaStream_t st) {
     if (pe <= pb || ke <= kb) return 0;
+    {
+        const int nj = e->phases[pe - 1].job_begin + e->phases[pe - 1].job_count - e->phases[pb].job_begin;
+        if (nj > kMaxJobs || pe - pb > kMaxPhases) return fail(SACB_ERR_INVALID, "program slice too large (%d jobs, %d phases)", nj, pe - pb);
+    }
     const bool single = (pe - pb == 1) && (ke - kb == 1);
     if (e->mode == 1 || single) {
         for (int k = kb; k < ke; ++k)
@@ -858,7 +881,7 @@ int sacb_update(sacb_handle e, int32_t n_updates, const int64_t* idx_in, const f
     ra.idx = idx; ra.idx_stride = B;
     ra.eps1 = eps; ra.eps2 = eps + (size_t)B * A; ra.eps_stride = 2LL * B * A;
     ra.loss_q_out = loss_q; ra.loss_pi_out = loss_pi;
-    ra.fuse_polyak = 1; ra.pass_mask = 3;
+    ra.fuse_polyak = 1; ra.pass_mask = 3; ra.k_total = n_updates;
     if (e->world <= 1) {
         if (int r = run_phases(e, ra, e->p_update.begin, e->p_update.end, 0, n_updates, st)) return r;
     } else {
@@ -1116,7 +1139,7 @@ int sacb_debug_profile(sacb_handle e, int32_t n_updates, uint64_t* out, int64_t 
     fill_args(e, ra);
     ra.idx = e->idx_buf; ra.idx_stride = B;
     ra.eps1 = e->eps_buf; ra.eps2 = e->eps_buf + (size_t)B * A; ra.eps_stride = 2LL * B * A;
-    ra.fuse_polyak = 1; ra.pass_mask = 3; ra.prof = d;
+    ra.fuse_polyak = 1; ra.pass_mask = 3; ra.prof = d; ra.k_total = n_updates;
     const int saved_mode = e->mode;
     e->mode = 0;
     int rc = run_phases(e, ra, e->p_update.begin, e->p_update.end, 0, n_updates, st);
@@ -1143,6 +1166,13 @@ int sacb_debug_profile(sacb_handle e, int32_t n_updates, uint64_t* out, int64_t 
 }
 
 int64_t sacb_launch_count(sacb_handle e) { return e ? e->launches : 0; }
+
+int sacb_set_precision(sacb_handle e, int32_t tf32x3) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (tf32x3 != 0 && tf32x3 != 1) return fail(SACB_ERR_INVALID, "precision must be 0 (fp32 FFMA) or 1 (3xTF32 tensor cores)");
+    e->tf32x3 = tf32x3;
+    return 0;
+}
 
 int sacb_set_mode(sacb_handle e, int32_t mode) {
     if (!e) return fail(SACB_ERR_INVALID, "null handle");

@@ -329,3 +329,7 @@ class Engine:
 
     def set_mode(self, mode):
         check(self._lib.sacb_set_mode(self._h, int(mode)))
+
+    def set_precision(self, tf32x3):
+        """1 (default): tensor-core GEMMs with 3xTF32 error compensation; 0: plain fp32 FFMA."""
+        check(self._lib.sacb_set_precision(self._h, int(tf32x3)))
