@@ -227,6 +227,7 @@ def run_gpu(args):
 
     eng = sac._engine(actor, critic, B, target=target, pi_opt=pi_opt, q_opt=q_opt)
     eng.set_mode(args.mode)
+    eng.set_precision(args.precision)
     run_updates(args.warmup, False)                                 # W untimed warm-up steps
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
@@ -262,7 +263,8 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 6), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "update_every": UPDATE_EVERY, "batch_per_gpu": B, "global_batch": B * world,
+        "config": {"workload": WORKLOAD, "update_every": UPDATE_EVERY, "batch_per_gpu": B,
+                   "gemm_arithmetic": "tensor-core 3xTF32 (fp32-level accuracy), fp32 accumulate" if args.precision else "fp32 FFMA", "global_batch": B * world,
                    "parallelism": f"dp{world}", "global_steps_per_s": round(args.steps / (ms * 1e-3), 1),
                    "samples_per_s": round(value * B, 1),
                    "l2_policy": "inputs larger than L2: 165 MB replay ring, random-row gather; the 3.2 MB of weights/Adam "
@@ -294,6 +296,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", type=int, default=0, help="profiling only: 1 = one kernel launch per phase")
     ap.add_argument("--no-cpu", action="store_true", help="profiling only: skip the cpu_baseline leg")
+    ap.add_argument("--precision", type=int, default=1, help="1 = tensor-core 3xTF32 GEMMs (default), 0 = fp32 FFMA")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -14,9 +14,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-PHASES = ["gather", "A.L0+C.L0", "A.L1+C.L1", "A.heads", "row_heads", "T.L0", "T.L1", "row_backup", "C.dW1+dh1+db1+dW2",
-          "C.dW0+db0+lossq", "adam_c+polyak", "Cpi.L0", "Cpi.L1", "row_pi", "Cpi.dh1", "dpi", "row_ghead", "A.dWh+dh2",
-          "A.dW1+dh1", "A.dW0+losspi", "adam_a"]
+PHASES = ["gather(first only)", "A.L0+C.L0", "A.L1(+heads)+C.L1q1", "rows_heads+C.L1q2", "T.L0", "T.L1", "row_backup",
+          "C.dh1+db1+dW2", "C.dW1+dW0+db0+lossq", "adam_c+polyak", "Cpi.L0", "Cpi.L1", "row_pi", "Cpi.dh1(+dpi)", "row_ghead",
+          "A.dWh+dh2", "A.dW1+dh1", "A.dW0+losspi", "adam_a+gather(k+1)"]
 
 
 def main():
@@ -44,21 +44,33 @@ def main():
     names = PHASES if nP == len(PHASES) else [f"p{i}" for i in range(nP)]
     work_end = st[..., 0].max(axis=2)                        # slowest CTA done with its tiles
     bar_end = st[..., 1].max(axis=2)                         # everyone past the barrier
-    first_work_end = st[..., 0].min(axis=2)
-    start = np.empty_like(bar_end)
-    start[:, 1:] = bar_end[:, :-1]
-    start[1:, 0] = bar_end[:-1, -1]
-    start[0, 0] = first_work_end[0, 0]
-    sl = slice(1, None) if n > 1 else slice(0, None)         # skip the first update (cold)
-    work = (work_end - start)[sl].mean(axis=0) / 1e3
-    barrier = (bar_end - work_end)[sl].mean(axis=0) / 1e3
-    fastest = (first_work_end - start)[sl].mean(axis=0) / 1e3
-    per_update = (bar_end[sl, -1] - start[sl, 0]).mean() / 1e3
-    print(f"# persistent sac_phase_kernel, {nC} CTAs, {nP} phases, mean over {work_end[sl].shape[0]} updates; microseconds")
-    print(f"{'phase':<22}{'work(max cta)':>14}{'work(min cta)':>14}{'barrier':>10}{'total':>9}")
+    first_work_end = np.where(st[..., 0] > 0, st[..., 0], np.iinfo(np.int64).max).min(axis=2)
+    work = np.zeros(nP); barrier = np.zeros(nP); fastest = np.zeros(nP); cnt = np.zeros(nP)
+    per_update = []
+    prev_end = None
+    for k in range(n):
+        t_start = None
+        for p in range(nP):
+            if work_end[k, p] == 0:                          # phase skipped for this update (initial gather)
+                continue
+            if prev_end is not None and k >= 1:
+                work[p] += work_end[k, p] - prev_end
+                fastest[p] += first_work_end[k, p] - prev_end
+                barrier[p] += max(bar_end[k, p], work_end[k, p]) - work_end[k, p]
+                cnt[p] += 1
+            if t_start is None:
+                t_start = prev_end
+            prev_end = max(bar_end[k, p], work_end[k, p])
+        if k >= 1 and t_start is not None:
+            per_update.append(prev_end - t_start)
+    cnt = np.maximum(cnt, 1)
+    work, barrier, fastest = work / cnt / 1e3, barrier / cnt / 1e3, fastest / cnt / 1e3
+    per_update = float(np.mean(per_update)) / 1e3
+    print(f"# persistent sac_phase_kernel, {nC} CTAs, {nP} phases, mean over {n - 1} updates (first skipped); microseconds")
+    print(f"{'phase':<24}{'work(max cta)':>14}{'work(min cta)':>14}{'barrier':>10}{'total':>9}")
     for i in range(nP):
-        print(f"{names[i]:<22}{work[i]:>14.2f}{fastest[i]:>14.2f}{barrier[i]:>10.2f}{work[i] + barrier[i]:>9.2f}")
-    print(f"{'SUM':<22}{work.sum():>14.2f}{'':>14}{barrier.sum():>10.2f}{(work + barrier).sum():>9.2f}")
+        print(f"{names[i]:<24}{work[i]:>14.2f}{fastest[i]:>14.2f}{barrier[i]:>10.2f}{work[i] + barrier[i]:>9.2f}")
+    print(f"{'SUM':<24}{work.sum():>14.2f}{'':>14}{barrier.sum():>10.2f}{(work + barrier).sum():>9.2f}")
     print(f"per update (stamps): {per_update:.2f} us  -> {1e6 / per_update:.0f} updates/s")
 
 

@@ -54,10 +54,10 @@ def _check(g, prefix, name, value, rtol, atol):
 
 
 @pytest.mark.parametrize("name", ["small", "ragged", "c1"])
-@pytest.mark.parametrize("mode,tf32x3", [(0, 1), (1, 1), (0, 0)])
+@pytest.mark.parametrize("mode,tf32x3", [(0, 1), (1, 1), (0, 0), (0, 2), (1, 2)])
 def test_update_matches_reference_golden(name, mode, tf32x3):
-    """mode 0 = persistent kernel, 1 = one launch per phase; tf32x3 1 = tensor-core GEMMs with 3xTF32 error
-    compensation (default), 0 = plain fp32 FFMA.  Same tolerances for both arithmetic paths."""
+    """mode 0 = persistent kernel, 1 = one launch per phase; tf32x3: 0 = plain fp32 FFMA, 1 = mma.sync tensor-core
+    GEMMs with 3xTF32 error compensation, 2 = tcgen05 (TMEM accumulators) with 3xTF32.  Same tolerances for all."""
     from torch_actor_critic_b200.engine import actor_views, critic_views
     g, actor, critic, arrays, hp = load_case(name)
     eng, av, cv, tv, adam = _engine_for(g, actor, critic, arrays, hp)
@@ -382,3 +382,46 @@ def test_errors_are_loud():
         Engine(3, 2, [8, 8, 8])
     with pytest.raises(_lib.SacbError):
         Engine(3, 2, [8, 8], flags=_lib.FLAG_PI_FROM_STATES)
+
+
+@pytest.mark.parametrize("tf32x3", [1, 0, 2])
+def test_humanoid_shaped_update_matches_oracle(tf32x3):
+    """BASELINE config 2 shapes (obs=376, act=17, MLP 512x512, batch=1024) in fp32 storage: one update vs the float64
+    oracle.  Exercises multi-tile heads (2A = 34 > 32), 16 partial-Q tiles and K = 393 / 512 / 1024 reductions."""
+    from torch_actor_critic_b200.engine import Engine, actor_views, critic_views
+    O, A, H, B, N = 376, 17, [512, 512], 1024, 4096
+    rng = np.random.default_rng(3)
+    actor, critic = onp.init_params(O, A, H, rng)
+    arrays = dict(state=rng.standard_normal((N, O)).astype(np.float32), actions=rng.uniform(-0.4, 0.4, (N, A)).astype(np.float32),
+                  rewards=rng.standard_normal(N).astype(np.float32), next_state=rng.standard_normal((N, O)).astype(np.float32),
+                  done=rng.random(N) < 0.05)
+    idx = rng.choice(N, B, replace=False)[None]
+    eps = rng.standard_normal((1, 2, B, A)).astype(np.float32)
+    eng = Engine(O, A, H, batch_size=B, max_burst=2, device=0, act_limit=0.4)
+    eng.set_precision(tf32x3)
+    pa, pc = eng.new_actor_arena(), eng.new_critic_arena()
+    for k, v in actor_views(eng.layout, pa, O, A, H).items():
+        v.copy_(torch.from_numpy(actor[k]))
+    for k, v in critic_views(eng.layout, pc, O, A, H).items():
+        v.copy_(torch.from_numpy(critic[k]))
+    pt = pc.clone()
+    eng.bind_params(pa, pc, pt)
+    eng.bind_adam(eng.new_actor_arena(), eng.new_actor_arena(), 0, eng.new_critic_arena(), eng.new_critic_arena(), 0)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in arrays.items()}
+    eng.bind_buffer(t["state"], t["actions"], t["rewards"], t["next_state"], t["done"])
+    eng.set_buffer_state(0, N)
+    lq, lp = eng.update(1, idx=idx, eps=eps)
+    hp = onp.HyperParams(act_limit=0.4)
+    a64, c64, t64 = (onp.cast_params(p, np.float64) for p in (actor, critic, critic))
+    o = onp.sac_update(a64, c64, t64, onp.AdamState.zeros_like(a64), onp.AdamState.zeros_like(c64),
+                       batch_from(arrays, idx[0], np.float64), eps[0, 0].astype(np.float64), eps[0, 1].astype(np.float64), hp)
+    assert_close(lq.cpu().numpy(), [o["loss_q"]], 2e-4, 2e-5, "loss_q")
+    assert_close(lp.cpu().numpy(), [o["loss_pi"]], 2e-4, 2e-5, "loss_pi")
+    for key in ("backup", "q1", "q2", "logp_next", "logp_pi", "q1_pi", "q2_pi", "a2", "pi"):
+        assert_close(eng.debug_read(key), o[key], 2e-4, 1e-4, key)
+    gc = critic_views(eng.layout, torch.from_numpy(eng.debug_read("grad_critic")), O, A, H)
+    for k in CRITIC_KEYS:
+        assert_close(gc[k].numpy(), o["critic_grads"][k], 2e-3, 5e-6, k)
+    ga = actor_views(eng.layout, torch.from_numpy(eng.debug_read("grad_actor")), O, A, H)
+    for k in ACTOR_KEYS:
+        assert_close(ga[k].numpy(), o["actor_grads"][k], 2e-3, 5e-6, k)

@@ -91,7 +91,8 @@ struct ProgRange { int begin = 0, end = 0; };
 struct sacb_engine {
     sacb_config cfg{};
     sacb_layout_info lay{};
-    int num_sms = 0, grid_coop = 0;
+    int num_sms = 0, grid_coop = 0, grid_std = 0, grid_t5 = 0;
+    int tile_m = kBM, tile_n = kBN;       // GEMM tile of the active arithmetic path (64x16 for tcgen05)
     int mode = 0;
     int tf32x3 = 1;                 // GEMM precision: 1 = tensor cores with 3xTF32 compensation, 0 = fp32 FFMA
     long long launches = 0;
@@ -107,7 +108,7 @@ struct sacb_engine {
     size_t ws_floats = 0;
     int ldx = 0, lds = 0, ldh = 0, lddpi = 0, tnH2 = 0, row_tiles = 0;
     float *xs, *xp, *x2, *s2buf, *rd, *ah1, *ah2, *heads, *logp, *ch1, *ch2, *th1, *th2, *qpart, *qtpart, *qbuf, *qfw,
-        *dh2, *dh1, *dpi, *ghead, *adh2, *adh1, *lparts_q, *lparts_pi, *loss_scalar, *ga, *gc;
+        *dh2, *dh1, *dpi, *ghead, *hpart, *dpart, *adh2, *adh1, *lparts_q, *lparts_pi, *loss_scalar, *ga, *gc;
     long long* idx_buf = nullptr;
     int* perm_buf = nullptr;
     size_t perm_cap = 0;
@@ -196,8 +197,8 @@ struct Builder {
         j.M = M; j.N = N; j.K = K; j.nz = nz; j.rows_dynamic = dyn;
         j.a_vec = al16(A) && (lda % 4 == 0) && (sA % 4 == 0);
         j.b_vec = al16(B) && (ldb % 4 == 0) && (sB % 4 == 0);
-        j.tn = (N + kBN - 1) / kBN;
-        j.tpz = ((M + kBM - 1) / kBM) * j.tn;
+        j.tn = (N + e->tile_n - 1) / e->tile_n;
+        j.tpz = ((M + e->tile_m - 1) / e->tile_m) * j.tn;
         j.ntiles = j.tpz * nz;
         if (nz > 2) { fprintf(stderr, "sacb: nz > 2 unsupported\n"); abort(); }
         return j;
@@ -210,198 +211,7 @@ struct Builder {
     }
 };
 
-static void build_programs(sacb_engine* e) {
-    e->jobs.clear();
-    e->phases.clear();
-    Builder b(e);
-    const sacb_config& c = e->cfg;
-    const sacb_layout_info& L = e->lay;
-    const int O = c.obs_dim, A = c.act_dim, H1 = c.hidden1, H2 = c.hidden2, B = c.batch_size;
-    const int OA = O + A, ldx = e->ldx, lds = e->lds, ldh = e->ldh, lddpi = e->lddpi;
-    float *PA = e->pa, *PC = e->pc, *PT = e->pt, *GA = e->ga, *GC = e->gc;
-    const long long sW1 = L.critic_w1[1] - L.critic_w1[0];
-    const int row_tiles = e->row_tiles;
-
-    auto actor_l0 = [&](int dyn) {
-        Job j = b.gemm(G_FWD, E_BIAS_RELU, e->s2buf, lds, 0, PA + L.actor_w0, O, 0, e->ah1, H1, 0, B, H1, O, 1, dyn);
-        j.bias = PA + L.actor_b0; return j; };
-    auto actor_l1 = [&](int dyn) {
-        Job j = b.gemm(G_FWD, E_BIAS_RELU, e->ah1, H1, 0, PA + L.actor_w1, H1, 0, e->ah2, H2, 0, B, H2, H1, 1, dyn);
-        j.bias = PA + L.actor_b1; return j; };
-    auto actor_heads = [&](int dyn) {
-        Job j = b.gemm(G_FWD, E_BIAS, e->ah2, H2, 0, PA + L.actor_w_mu, H2, 0, e->heads, ldh, 0, B, 2 * A, H2, 1, dyn);
-        j.bias = PA + L.actor_b_mu; return j; };
-    auto row_heads = [&](int dyn) {
-        Job j = Builder::zero();
-        j.type = J_ROW_HEADS; j.A = e->heads; j.lda = ldh; j.M = B; j.rows_dynamic = dyn;
-        j.out0 = e->x2; j.out1 = e->logp; j.out2 = e->xp; j.out3 = e->logp + B; j.ldc = ldx; j.i0 = O;
-        j.ntiles = (B + 7) / 8; return j; };
-    auto critic_l0 = [&](float* P, const float* X, float* H, int dyn) {
-        Job j = b.gemm(G_FWD, E_BIAS_RELU, X, ldx, 0, P + L.critic_w0[0], OA, 0, H, 2 * H1, 0, B, 2 * H1, OA, 1, dyn);
-        j.bias = P + L.critic_b0[0]; return j; };
-    auto critic_l1 = [&](float* P, const float* Hin, float* Hout, float* part, int dyn) {
-        Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, Hin, 2 * H1, H1, P + L.critic_w1[0], H1, sW1, Hout, 2 * H2, H2, B, H2, H1, 2, dyn);
-        j.bias = P + L.critic_b1[0]; j.sBias = H2; j.aux0 = P + L.critic_w2[0]; j.sAux = H2; j.out0 = part; j.i0 = B;
-        return j; };
-    auto critic_dx1 = [&]() {       // dh1 = (dh2 . W1) * relu'(h1)
-        Job j = b.gemm(G_DX, E_MASK, e->dh2, 2 * H2, H2, PC + L.critic_w1[0], H1, sW1, e->dh1, 2 * H1, H1, B, H1, H2, 2);
-        j.mask = e->ch1; j.ldmask = 2 * H1; j.sMask = H1; return j; };
-
-    // ---------------- full update: sample/gather -> update_critic -> update_policy -> update_targets ----------------
-    e->p_update.begin = (int)e->phases.size();
-    auto gather = [&](int k_offset) {
-        Job j = Builder::zero();
-        j.type = J_GATHER; j.M = B; j.C = e->xs; j.out0 = e->xp; j.out1 = e->x2; j.ldc = ldx; j.out2 = e->s2buf; j.ldb = lds;
-        j.out3 = e->rd; j.ntiles = (B + 7) / 8; j.k_offset = k_offset;
-        return j; };
-    {   // P0 gather (ReplayBuffer.sample, buffer/replay_buffer.py:45-54).  Runs for the first update of a launch only:
-        // every later batch is prefetched by the last phase of the previous update (the indices of the whole burst
-        // are known up front), so the HBM latency of the random-row gather is off the critical path.
-        int p0 = b.phase();
-        e->phases[p0].pad = 1;
-        b.add(gather(0));
-    }
-    e->ph_crit_begin = (int)e->phases.size();
-    b.phase(); b.add(actor_l0(0)); b.add(critic_l0(PC, e->xs, e->ch1, 0));                 // P1
-    b.phase(); b.add(actor_l1(0)); b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0));      // P2
-    b.phase(); b.add(actor_heads(0));                                                       // P3
-    b.phase(); b.add(row_heads(0));                                                         // P4
-    b.phase(); b.add(critic_l0(PT, e->x2, e->th1, 0));                                      // P5 target critic on (s', a2)
-    b.phase(); b.add(critic_l1(PT, e->th1, e->th2, e->qtpart, 0));                          // P6
-    {   // P7 backup + dq + dh2 (sac/algorithm.py:63-72)
-        b.phase();
-        Job j = Builder::zero();
-        j.type = J_ROW_BACKUP; j.M = B; j.A = e->qpart; j.B = e->qtpart; j.i0 = B; j.i1 = e->tnH2;
-        j.bias = PC + L.critic_b2[0]; j.aux0 = PT + L.critic_b2[0]; j.aux1 = PC + L.critic_w2[0];
-        j.mask = e->ch2; j.ldmask = 2 * H2; j.C = e->dh2; j.ldc = 2 * H2; j.out0 = e->qbuf; j.out1 = e->lparts_q;
-        j.out2 = e->logp; j.aux2 = e->rd; j.aux3 = e->rd + B; j.ntiles = row_tiles;
-        b.add(j);
-    }
-    {   // P8 critic layer-1 grads + dh1
-        b.phase();
-        b.add(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2));
-        b.add(critic_dx1());
-        b.add(b.colsum(e->dh2, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, B, 2 * H2, 1));
-        b.add(b.colsum(e->ch2, 2 * H2, H2, e->qbuf + 5 * (size_t)B, B, GC + L.critic_w2[0], H2, B, H2, 2));
-    }
-    {   // P9 critic layer-0 grads, loss
-        b.phase();
-        b.add(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1));
-        b.add(b.colsum(e->dh1, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, B, 2 * H1, 1));
-        Job j = Builder::zero();
-        j.type = J_REDUCE_Q; j.A = e->lparts_q; j.i0 = row_tiles; j.out0 = e->loss_scalar; j.out1 = GC + L.critic_b2[0];
-        j.out2 = GC + L.critic_b2[1]; j.ntiles = 1;
-        b.add(j);
-    }
-    e->ph_crit_adam = (int)e->phases.size();
-    {   // P10 Adam(critic) [+ Polyak]
-        b.phase();
-        Job j = Builder::zero();
-        j.type = J_ADAM; j.C = PC; j.A = GC; j.out0 = e->mc; j.out1 = e->vc; j.out2 = PT; j.K = (int)L.critic_floats; j.i0 = 1;
-        j.ntiles = (int)((L.critic_floats + kThreads * 4 - 1) / (kThreads * 4));
-        b.add(j);
-    }
-    auto policy_tail = [&]() {
-        b.phase(); b.add(critic_l0(PC, e->xp, e->ch1, 0));                                  // critic on (s, pi)
-        b.phase(); b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0));
-        {
-            b.phase();
-            Job j = Builder::zero();
-            j.type = J_ROW_PI; j.M = B; j.A = e->qpart; j.i0 = B; j.i1 = e->tnH2; j.bias = PC + L.critic_b2[0];
-            j.aux1 = PC + L.critic_w2[0]; j.mask = e->ch2; j.ldmask = 2 * H2; j.C = e->dh2; j.ldc = 2 * H2;
-            j.out0 = e->qbuf; j.out1 = e->lparts_pi; j.aux2 = e->logp + B; j.ntiles = row_tiles;
-            b.add(j);
-        }
-        b.phase(); b.add(critic_dx1());
-        b.phase();      // dpi = dh1 . W0[:, O:O+A]   (both critics at once: reduction over 2*H1)
-        b.add(b.gemm(G_DX, E_STORE, e->dh1, 2 * H1, 0, PC + L.critic_w0[0] + O, OA, 0, e->dpi, lddpi, 0, B, A, 2 * H1, 1));
-        {
-            b.phase();
-            Job j = Builder::zero();
-            j.type = J_ROW_GHEAD; j.M = B; j.A = e->heads; j.lda = ldh; j.B = e->dpi; j.ldb = lddpi; j.C = e->ghead; j.ldc = ldh;
-            j.ntiles = (B + 15) / 16;
-            b.add(j);
-        }
-        {
-            b.phase();
-            b.add(b.gemm(G_DW, E_STORE, e->ghead, ldh, 0, e->ah2, H2, 0, GA + L.actor_w_mu, H2, 0, 2 * A, H2, B, 1));
-            b.add(b.colsum(e->ghead, ldh, 0, nullptr, 0, GA + L.actor_b_mu, 0, B, 2 * A, 1));
-            Job j = b.gemm(G_DX, E_MASK, e->ghead, ldh, 0, PA + L.actor_w_mu, H2, 0, e->adh2, H2, 0, B, H2, 2 * A, 1);
-            j.mask = e->ah2; j.ldmask = H2;
-            b.add(j);
-        }
-        {
-            b.phase();
-            b.add(b.gemm(G_DW, E_STORE, e->adh2, H2, 0, e->ah1, H1, 0, GA + L.actor_w1, H1, 0, H2, H1, B, 1));
-            b.add(b.colsum(e->adh2, H2, 0, nullptr, 0, GA + L.actor_b1, 0, B, H2, 1));
-            Job j = b.gemm(G_DX, E_MASK, e->adh2, H2, 0, PA + L.actor_w1, H1, 0, e->adh1, H1, 0, B, H1, H2, 1);
-            j.mask = e->ah1; j.ldmask = H1;
-            b.add(j);
-        }
-        {
-            b.phase();
-            b.add(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->s2buf, lds, 0, GA + L.actor_w0, O, 0, H1, O, B, 1));
-            b.add(b.colsum(e->adh1, H1, 0, nullptr, 0, GA + L.actor_b0, 0, B, H1, 1));
-            Job j = Builder::zero();
-            j.type = J_REDUCE_PI; j.A = e->lparts_pi; j.i0 = row_tiles; j.out0 = e->loss_scalar + 1; j.ntiles = 1;
-            b.add(j);
-        }
-        int adam_phase = b.phase();
-        {
-            Job j = Builder::zero();
-            j.type = J_ADAM; j.C = PA; j.A = GA; j.out0 = e->ma; j.out1 = e->va; j.out2 = nullptr; j.K = (int)L.actor_floats; j.i0 = 0;
-            j.ntiles = (int)((L.actor_floats + kThreads * 4 - 1) / (kThreads * 4));
-            b.add(j);
-        }
-        return adam_phase;
-    };
-    e->ph_pi_begin = (int)e->phases.size();
-    e->ph_pi_adam = policy_tail();
-    b.add(gather(1));                                      // prefetch the next update's batch (staging tiles are idle here)
-    e->p_update.end = (int)e->phases.size();
-
-    // ---------------- standalone update_policy (actor trunk recomputed) ----------------
-    e->p_policy.begin = (int)e->phases.size();
-    b.phase(); b.add(actor_l0(0));
-    b.phase(); b.add(actor_l1(0));
-    b.phase(); b.add(actor_heads(0));
-    b.phase(); b.add(row_heads(0));
-    policy_tail();
-    e->p_policy.end = (int)e->phases.size();
-
-    // ---------------- update_targets ----------------
-    e->p_targets.begin = (int)e->phases.size();
-    {
-        b.phase();
-        Job j = Builder::zero();
-        j.type = J_POLYAK; j.C = PT; j.A = PC; j.K = (int)L.critic_floats;
-        j.ntiles = (int)((L.critic_floats + kThreads * 4 - 1) / (kThreads * 4));
-        b.add(j);
-    }
-    e->p_targets.end = (int)e->phases.size();
-
-    // ---------------- forward-only programs (dynamic row count) ----------------
-    e->p_actor_fwd.begin = (int)e->phases.size();
-    b.phase(); b.add(actor_l0(1));
-    b.phase(); b.add(actor_l1(1));
-    b.phase(); b.add(actor_heads(1));
-    b.phase(); b.add(row_heads(1));
-    e->p_actor_fwd.end = (int)e->phases.size();
-    for (int w = 0; w < 2; ++w) {
-        float* P = w ? PT : PC;
-        e->p_critic_fwd[w].begin = (int)e->phases.size();
-        b.phase(); b.add(critic_l0(P, e->xs, e->ch1, 1));
-        b.phase(); b.add(critic_l1(P, e->ch1, e->ch2, e->qpart, 1));
-        {
-            b.phase();
-            Job j = Builder::zero();
-            j.type = J_ROW_QSUM; j.M = B; j.rows_dynamic = 1; j.A = e->qpart; j.i0 = B; j.i1 = e->tnH2;
-            j.bias = P + L.critic_b2[0]; j.out0 = e->qfw; j.ntiles = (B + kThreads - 1) / kThreads;
-            b.add(j);
-        }
-        e->p_critic_fwd[w].end = (int)e->phases.size();
-    }
-}
+#include "sacb_program.inl"
 
 static int upload_programs(sacb_engine* e, cudaStream_t st) {
     if (!e->dirty) return 0;
@@ -568,7 +378,7 @@ static int run_phases(sacb_engine* e, RunArgs ra, int pb, int pe, int kb, int ke
                 ra.phase_begin = p; ra.phase_end = p + 1; ra.k_begin = k; ra.k_end = k + 1; ra.use_barrier = 0;
                 int nt = e->phases[p].ntiles;
                 int grid = nt < 1 ? 1 : nt;
-                sac_phase_kernel<<<grid, kThreads, kSmemBytes, st>>>(ra);
+                sac_phase_kernel<<<grid, kThreads, e->tf32x3 == 2 ? kSmemBytesT5 : kSmemBytes, st>>>(ra);
                 CU(cudaGetLastError());
                 e->launches++;
             }
@@ -577,7 +387,8 @@ static int run_phases(sacb_engine* e, RunArgs ra, int pb, int pe, int kb, int ke
     ra.phase_begin = pb; ra.phase_end = pe; ra.k_begin = kb; ra.k_end = ke; ra.use_barrier = 1;
     CU(cudaMemsetAsync(e->barrier, 0, sizeof(unsigned long long), st));
     void* args[] = {&ra};
-    CU(cudaLaunchCooperativeKernel((void*)sac_phase_kernel, dim3(e->grid_coop), dim3(kThreads), args, kSmemBytes, st));
+    CU(cudaLaunchCooperativeKernel((void*)sac_phase_kernel, dim3(e->grid_coop), dim3(kThreads), args,
+                                   e->tf32x3 == 2 ? kSmemBytesT5 : kSmemBytes, st));
     e->launches++;
     return 0;
 }
@@ -615,17 +426,22 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, cfg->device));
     e->num_sms = prop.multiProcessorCount;
-    CU(cudaFuncSetAttribute(sac_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CU(cudaFuncSetAttribute(sac_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesT5));
     CU(cudaFuncSetAttribute(draw_indices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * (int)sizeof(long long)));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sac_phase_kernel, kThreads, kSmemBytes));
     if (occ < 1) { delete e; return fail(SACB_ERR_CUDA, "sac_phase_kernel does not fit on an SM"); }
     if (occ > 2) occ = 2;
-    e->grid_coop = occ * e->num_sms;
+    e->grid_std = occ * e->num_sms;
+    int occ5 = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ5, sac_phase_kernel, kThreads, kSmemBytesT5));
+    e->grid_t5 = (occ5 < 1 ? 0 : 1) * e->num_sms;
+    e->grid_coop = e->grid_std;
 
     const long long O = cfg->obs_dim, A = cfg->act_dim, H1 = cfg->hidden1, H2 = cfg->hidden2, B = cfg->batch_size;
     e->ldx = (int)r4(O + A); e->lds = (int)r4(O); e->ldh = (int)r4(2 * A); e->lddpi = (int)r4(A);
-    e->tnH2 = (int)((H2 + kBN - 1) / kBN);
+    e->tnH2 = (int)((H2 + e->tile_n - 1) / e->tile_n);
+    const long long tn16_H2 = (H2 + 15) / 16, tn16_H1 = (H1 + 15) / 16;     // partial-tile counts of the finest tiling (tcgen05: N=16)
     e->row_tiles = (int)((B + 7) / 8);
     // carve the workspace
     size_t off = 0;
@@ -636,9 +452,10 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     want(e->xs, B * e->ldx); want(e->xp, B * e->ldx); want(e->x2, B * e->ldx); want(e->s2buf, B * e->lds); want(e->rd, 2 * B);
     want(e->ah1, B * H1); want(e->ah2, B * H2); want(e->heads, B * e->ldh); want(e->logp, 2 * B);
     want(e->ch1, B * 2 * H1); want(e->ch2, B * 2 * H2); want(e->th1, B * 2 * H1); want(e->th2, B * 2 * H2);
-    want(e->qpart, 2LL * e->tnH2 * B); want(e->qtpart, 2LL * e->tnH2 * B); want(e->qbuf, 9 * B); want(e->qfw, 2 * B);
+    want(e->qpart, 2LL * tn16_H2 * B); want(e->qtpart, 2LL * tn16_H2 * B); want(e->qbuf, 9 * B); want(e->qfw, 2 * B);
     want(e->dh2, B * 2 * H2); want(e->dh1, B * 2 * H1); want(e->dpi, B * e->lddpi); want(e->ghead, B * e->ldh);
     want(e->adh2, B * H2); want(e->adh1, B * H1);
+    want(e->hpart, tn16_H2 * 2 * A * B); want(e->dpart, 2LL * tn16_H1 * A * B);
     want(e->lparts_q, 4LL * e->row_tiles); want(e->lparts_pi, 4LL * e->row_tiles); want(e->loss_scalar, 4);
     want(e->ga, e->lay.actor_floats); want(e->gc, e->lay.critic_floats);
     e->ws_floats = off;
@@ -1169,8 +986,14 @@ int64_t sacb_launch_count(sacb_handle e) { return e ? e->launches : 0; }
 
 int sacb_set_precision(sacb_handle e, int32_t tf32x3) {
     if (!e) return fail(SACB_ERR_INVALID, "null handle");
-    if (tf32x3 != 0 && tf32x3 != 1) return fail(SACB_ERR_INVALID, "precision must be 0 (fp32 FFMA) or 1 (3xTF32 tensor cores)");
+    if (tf32x3 < 0 || tf32x3 > 2) return fail(SACB_ERR_INVALID, "precision must be 0 (fp32 FFMA), 1 (3xTF32 mma.sync) or 2 (3xTF32 tcgen05)");
+    if (tf32x3 == 2 && e->grid_t5 < 1) return fail(SACB_ERR_CUDA, "tcgen05 path does not fit on this device");
     e->tf32x3 = tf32x3;
+    e->tile_m = tf32x3 == 2 ? 64 : kBM;
+    e->tile_n = tf32x3 == 2 ? 16 : kBN;
+    e->tnH2 = (e->cfg.hidden2 + e->tile_n - 1) / e->tile_n;
+    e->grid_coop = tf32x3 == 2 ? e->grid_t5 : e->grid_std;
+    e->dirty = true;                                   // tile shapes are baked into the phase programs
     return 0;
 }
 

@@ -1,0 +1,239 @@
+// sacb_program.inl -- the phase programs (included by sacb_engine.cu after Builder / sacb_engine are defined).
+//
+// Program of ONE SAC gradient update (reference sac/algorithm.py:275-278), 18 grid-synchronised phases:
+//
+//   P0*  gather(k)                                   (* first update of a launch only; later batches are prefetched)
+//   ---- update_critic (sac/algorithm.py:115-141) ----
+//   P1   A.L0 (s' -> ah1)                  ||  C.L0 twin ([s|a] -> ch1)
+//   P2   A.L1 (+ heads as post-product)    ||  C.L1[q1] (+ Q-dot)
+//   P3   tanh-Gaussian rows (a2, logp | pi, logp)  ||  C.L1[q2] (+ Q-dot)
+//   P4   T.L0 twin ([s'|a2] -> th1)
+//   P5   T.L1 twin (+ Q-dot)
+//   P6   backup / dq / dh2 rows
+//   P7   C.dh1 twin  ||  db1  ||  dW2
+//   P8   C.dW1 twin  ||  C.dW0  ||  db0  ||  loss_q, db2
+//   P9   [NCCL]  Adam(critic) + Polyak
+//   ---- update_policy (sac/algorithm.py:143-162) ----
+//   P10  Cpi.L0 twin ([s|pi] -> ch1)
+//   P11  Cpi.L1 twin (+ Q-dot)
+//   P12  min-Q rows (loss_pi parts, dq routing, dh2)
+//   P13  Cpi.dh1 twin (+ d pi as post-product over the action columns of W0)
+//   P14  head-gradient rows (g_mu, g_ls)
+//   P15  A.dWh || dbh || A.dh2
+//   P16  A.dW1 || db1 || A.dh1
+//   P17  A.dW0 || db0 || loss_pi
+//   P18  [NCCL]  Adam(actor)  ||  gather(k+1)
+//
+// The two post-products need 2A <= 16 resp. A <= 16; wider action spaces fall back to a separate heads GEMM / d-pi
+// GEMM phase (generic path, exercised by the Humanoid-shaped test).
+
+static void build_programs(sacb_engine* e) {
+    e->jobs.clear();
+    e->phases.clear();
+    Builder b(e);
+    const sacb_config& c = e->cfg;
+    const sacb_layout_info& L = e->lay;
+    const int O = c.obs_dim, A = c.act_dim, H1 = c.hidden1, H2 = c.hidden2, B = c.batch_size;
+    const int OA = O + A, ldx = e->ldx, lds = e->lds, ldh = e->ldh, lddpi = e->lddpi;
+    float *PA = e->pa, *PC = e->pc, *PT = e->pt, *GA = e->ga, *GC = e->gc;
+    const long long sW1 = L.critic_w1[1] - L.critic_w1[0];
+    const int row_tiles = e->row_tiles;
+    const bool fuse_heads = 2 * A <= 16, fuse_dpi = A <= 16;
+    const int tnH1 = (H1 + e->tile_n - 1) / e->tile_n;
+
+    // ---- job factories -------------------------------------------------------------------------------------------
+    auto actor_l0 = [&](int dyn, int b_static) {
+        Job j = b.gemm(G_FWD, E_BIAS_RELU, e->s2buf, lds, 0, PA + L.actor_w0, O, 0, e->ah1, H1, 0, B, H1, O, 1, dyn);
+        j.bias = PA + L.actor_b0; j.b_static = b_static; return j; };
+    auto actor_l1 = [&](int dyn) {
+        Job j = b.gemm(G_FWD, E_BIAS_RELU, e->ah1, H1, 0, PA + L.actor_w1, H1, 0, e->ah2, H2, 0, B, H2, H1, 1, dyn);
+        j.bias = PA + L.actor_b1; j.b_static = 1;
+        if (fuse_heads) {        // post-product: heads partials [tile][2A][B] = h2 tile . [W_mu ; W_ls] slice
+            j.i1 = 2 * A; j.aux1 = PA + L.actor_w_mu; j.i2 = H2; j.i3 = 0; j.out1 = e->hpart; j.i0 = B;
+        }
+        return j; };
+    auto actor_heads = [&](int dyn) {
+        Job j = b.gemm(G_FWD, E_BIAS, e->ah2, H2, 0, PA + L.actor_w_mu, H2, 0, e->heads, ldh, 0, B, 2 * A, H2, 1, dyn);
+        j.bias = PA + L.actor_b_mu; j.b_static = 1; return j; };
+    auto row_heads = [&](int dyn) {
+        Job j = Builder::zero();
+        j.type = J_ROW_HEADS; j.A = e->heads; j.C = e->heads; j.lda = ldh; j.M = B; j.rows_dynamic = dyn;
+        j.out0 = e->x2; j.out1 = e->logp; j.out2 = e->xp; j.out3 = e->logp + B; j.ldc = ldx; j.i0 = O;
+        if (fuse_heads) { j.i1 = e->tnH2; j.B = e->hpart; j.i2 = B; j.bias = PA + L.actor_b_mu; }
+        j.ntiles = (B + 7) / 8; return j; };
+    auto critic_l0 = [&](float* P, const float* X, float* H, int dyn, int b_static) {
+        Job j = b.gemm(G_FWD, E_BIAS_RELU, X, ldx, 0, P + L.critic_w0[0], OA, 0, H, 2 * H1, 0, B, 2 * H1, OA, 1, dyn);
+        j.bias = P + L.critic_b0[0]; j.b_static = b_static; return j; };
+    // z0 .. z0+nz-1 of the twin layer 1 (with the Q-dot epilogue)
+    auto critic_l1 = [&](float* P, const float* Hin, float* Hout, float* part, int dyn, int z0, int nz) {
+        Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, Hin + (size_t)z0 * H1, 2 * H1, H1, P + L.critic_w1[z0], H1, sW1,
+                       Hout + (size_t)z0 * H2, 2 * H2, H2, B, H2, H1, nz, dyn);
+        j.bias = P + L.critic_b1[z0]; j.sBias = H2; j.aux0 = P + L.critic_w2[z0]; j.sAux = H2;
+        j.out0 = part + (size_t)z0 * e->tnH2 * B; j.i0 = B; j.b_static = 1;
+        return j; };
+    auto critic_dx1 = [&](bool with_dpi) {       // dh1 = (dh2 . W1) * relu'(h1)   [+ d pi partials]
+        Job j = b.gemm(G_DX, E_MASK, e->dh2, 2 * H2, H2, PC + L.critic_w1[0], H1, sW1, e->dh1, 2 * H1, H1, B, H1, H2, 2);
+        j.mask = e->ch1; j.ldmask = 2 * H1; j.sMask = H1; j.b_static = 1;
+        if (with_dpi && fuse_dpi) {   // X[n][a] = W0cat[(z*H1 + n), O + a]: z stride H1 rows of OA floats
+            j.i1 = A; j.aux1 = PC + L.critic_w0[0] + O; j.i2 = OA; j.i3 = 1; j.sAux = (long long)H1 * OA; j.out1 = e->dpart; j.i0 = B;
+        }
+        return j; };
+    auto gather = [&](int k_offset) {
+        Job j = Builder::zero();
+        j.type = J_GATHER; j.M = B; j.C = e->xs; j.out0 = e->xp; j.out1 = e->x2; j.ldc = ldx; j.out2 = e->s2buf; j.ldb = lds;
+        j.out3 = e->rd; j.ntiles = (B + 7) / 8; j.k_offset = k_offset;
+        return j; };
+    auto adam = [&](bool critic) {
+        Job j = Builder::zero();
+        j.type = J_ADAM;
+        if (critic) { j.C = PC; j.A = GC; j.out0 = e->mc; j.out1 = e->vc; j.out2 = PT; j.K = (int)L.critic_floats; j.i0 = 1; }
+        else { j.C = PA; j.A = GA; j.out0 = e->ma; j.out1 = e->va; j.out2 = nullptr; j.K = (int)L.actor_floats; j.i0 = 0; }
+        j.ntiles = (j.K + kThreads * 4 - 1) / (kThreads * 4);
+        return j; };
+
+    // actor trunk + heads + tanh-Gaussian rows; `with_critic` interleaves the online critic's forward (update_critic)
+    auto actor_forward = [&](int dyn, bool with_critic, int l0_static) {
+        b.phase(); b.add(actor_l0(dyn, l0_static)); if (with_critic) b.add(critic_l0(PC, e->xs, e->ch1, 0, 1));
+        b.phase(); b.add(actor_l1(dyn)); if (with_critic) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 1));
+        if (!fuse_heads) { b.phase(); b.add(actor_heads(dyn)); if (with_critic) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1)); }
+        b.phase(); b.add(row_heads(dyn));
+        if (with_critic && fuse_heads) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1));
+    };
+
+    // update_policy from "critic on (s, pi)" to Adam(actor); returns the Adam phase index
+    auto policy_tail = [&](bool first_static) {
+        b.phase(); b.add(critic_l0(PC, e->xp, e->ch1, 0, first_static ? 1 : 0));            // critic weights were just written by Adam
+        b.phase(); b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 2));
+        {
+            b.phase();
+            Job j = Builder::zero();
+            j.type = J_ROW_PI; j.M = B; j.A = e->qpart; j.i0 = B; j.i1 = e->tnH2; j.bias = PC + L.critic_b2[0];
+            j.aux1 = PC + L.critic_w2[0]; j.mask = e->ch2; j.ldmask = 2 * H2; j.C = e->dh2; j.ldc = 2 * H2;
+            j.out0 = e->qbuf; j.out1 = e->lparts_pi; j.aux2 = e->logp + B; j.ntiles = row_tiles;
+            b.add(j);
+        }
+        b.phase(); b.add(critic_dx1(true));
+        if (!fuse_dpi) {   // d pi = dh1 . W0[:, O:O+A]   (both critics at once: reduction over 2*H1)
+            b.phase();
+            Job j = b.gemm(G_DX, E_STORE, e->dh1, 2 * H1, 0, PC + L.critic_w0[0] + O, OA, 0, e->dpi, lddpi, 0, B, A, 2 * H1, 1);
+            j.b_static = 1;
+            b.add(j);
+        }
+        {
+            b.phase();
+            Job j = Builder::zero();
+            j.type = J_ROW_GHEAD; j.M = B; j.A = e->heads; j.lda = ldh; j.B = e->dpi; j.ldb = lddpi; j.C = e->ghead; j.ldc = ldh;
+            if (fuse_dpi) { j.i1 = 2 * tnH1; j.B = e->dpart; j.i2 = B; }
+            j.ntiles = (B + 15) / 16;
+            b.add(j);
+        }
+        {
+            b.phase();
+            b.add(b.gemm(G_DW, E_STORE, e->ghead, ldh, 0, e->ah2, H2, 0, GA + L.actor_w_mu, H2, 0, 2 * A, H2, B, 1));
+            b.add(b.colsum(e->ghead, ldh, 0, nullptr, 0, GA + L.actor_b_mu, 0, B, 2 * A, 1));
+            Job j = b.gemm(G_DX, E_MASK, e->ghead, ldh, 0, PA + L.actor_w_mu, H2, 0, e->adh2, H2, 0, B, H2, 2 * A, 1);
+            j.mask = e->ah2; j.ldmask = H2; j.b_static = 1;
+            b.add(j);
+        }
+        {
+            b.phase();
+            b.add(b.gemm(G_DW, E_STORE, e->adh2, H2, 0, e->ah1, H1, 0, GA + L.actor_w1, H1, 0, H2, H1, B, 1));
+            b.add(b.colsum(e->adh2, H2, 0, nullptr, 0, GA + L.actor_b1, 0, B, H2, 1));
+            Job j = b.gemm(G_DX, E_MASK, e->adh2, H2, 0, PA + L.actor_w1, H1, 0, e->adh1, H1, 0, B, H1, H2, 1);
+            j.mask = e->ah1; j.ldmask = H1; j.b_static = 1;
+            b.add(j);
+        }
+        {
+            b.phase();
+            b.add(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->s2buf, lds, 0, GA + L.actor_w0, O, 0, H1, O, B, 1));
+            b.add(b.colsum(e->adh1, H1, 0, nullptr, 0, GA + L.actor_b0, 0, B, H1, 1));
+            Job j = Builder::zero();
+            j.type = J_REDUCE_PI; j.A = e->lparts_pi; j.i0 = row_tiles; j.out0 = e->loss_scalar + 1; j.ntiles = 1;
+            b.add(j);
+        }
+        int adam_phase = b.phase();
+        b.add(adam(false));
+        return adam_phase;
+    };
+
+    // ---------------- full update: sample/gather -> update_critic -> update_policy -> update_targets ----------------
+    e->p_update.begin = (int)e->phases.size();
+    {   // P0 gather (ReplayBuffer.sample, buffer/replay_buffer.py:45-54).  Runs for the first update of a launch only:
+        // every later batch is prefetched by the last phase of the previous update (the indices of the whole burst
+        // are known up front), so the HBM latency of the random-row gather is off the critical path.
+        int p0 = b.phase();
+        e->phases[p0].pad = 1;
+        b.add(gather(0));
+    }
+    e->ph_crit_begin = (int)e->phases.size();
+    actor_forward(0, true, /*actor W0 was just written by Adam(actor) of the previous update*/ 0);
+    b.phase(); b.add(critic_l0(PT, e->x2, e->th1, 0, 1));                                   // target critic on (s', a2)
+    b.phase(); b.add(critic_l1(PT, e->th1, e->th2, e->qtpart, 0, 0, 2));
+    {   // backup + dq + dh2 (sac/algorithm.py:63-72)
+        b.phase();
+        Job j = Builder::zero();
+        j.type = J_ROW_BACKUP; j.M = B; j.A = e->qpart; j.B = e->qtpart; j.i0 = B; j.i1 = e->tnH2;
+        j.bias = PC + L.critic_b2[0]; j.aux0 = PT + L.critic_b2[0]; j.aux1 = PC + L.critic_w2[0];
+        j.mask = e->ch2; j.ldmask = 2 * H2; j.C = e->dh2; j.ldc = 2 * H2; j.out0 = e->qbuf; j.out1 = e->lparts_q;
+        j.out2 = e->logp; j.aux2 = e->rd; j.aux3 = e->rd + B; j.ntiles = row_tiles;
+        b.add(j);
+    }
+    {   // dh1 first (layer-0 gradients need it), bias / head-weight gradients ride along
+        b.phase();
+        b.add(critic_dx1(false));
+        b.add(b.colsum(e->dh2, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, B, 2 * H2, 1));
+        b.add(b.colsum(e->ch2, 2 * H2, H2, e->qbuf + 5 * (size_t)B, B, GC + L.critic_w2[0], H2, B, H2, 2));
+    }
+    {   // weight gradients of both layers, loss
+        b.phase();
+        b.add(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2));
+        b.add(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1));
+        b.add(b.colsum(e->dh1, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, B, 2 * H1, 1));
+        Job j = Builder::zero();
+        j.type = J_REDUCE_Q; j.A = e->lparts_q; j.i0 = row_tiles; j.out0 = e->loss_scalar; j.out1 = GC + L.critic_b2[0];
+        j.out2 = GC + L.critic_b2[1]; j.ntiles = 1;
+        b.add(j);
+    }
+    e->ph_crit_adam = (int)e->phases.size();
+    b.phase(); b.add(adam(true));                                                            // Adam(critic) [+ Polyak]
+    e->ph_pi_begin = (int)e->phases.size();
+    e->ph_pi_adam = policy_tail(false);
+    b.add(gather(1));                                      // prefetch the next update's batch (staging tiles are idle here)
+    e->p_update.end = (int)e->phases.size();
+
+    // ---------------- standalone update_policy (actor trunk recomputed) ----------------
+    e->p_policy.begin = (int)e->phases.size();
+    actor_forward(0, false, 0);
+    policy_tail(true);
+    e->p_policy.end = (int)e->phases.size();
+
+    // ---------------- update_targets ----------------
+    e->p_targets.begin = (int)e->phases.size();
+    {
+        b.phase();
+        Job j = Builder::zero();
+        j.type = J_POLYAK; j.C = PT; j.A = PC; j.K = (int)L.critic_floats;
+        j.ntiles = (int)((L.critic_floats + kThreads * 4 - 1) / (kThreads * 4));
+        b.add(j);
+    }
+    e->p_targets.end = (int)e->phases.size();
+
+    // ---------------- forward-only programs (dynamic row count) ----------------
+    e->p_actor_fwd.begin = (int)e->phases.size();
+    actor_forward(1, false, 0);
+    e->p_actor_fwd.end = (int)e->phases.size();
+    for (int w = 0; w < 2; ++w) {
+        float* P = w ? PT : PC;
+        e->p_critic_fwd[w].begin = (int)e->phases.size();
+        b.phase(); b.add(critic_l0(P, e->xs, e->ch1, 1, 0));
+        { b.phase(); Job j = critic_l1(P, e->ch1, e->ch2, e->qpart, 1, 0, 2); j.b_static = 0; b.add(j); }
+        {
+            b.phase();
+            Job j = Builder::zero();
+            j.type = J_ROW_QSUM; j.M = B; j.rows_dynamic = 1; j.A = e->qpart; j.i0 = B; j.i1 = e->tnH2;
+            j.bias = P + L.critic_b2[0]; j.out0 = e->qfw; j.ntiles = (B + 7) / 8;
+            b.add(j);
+        }
+        e->p_critic_fwd[w].end = (int)e->phases.size();
+    }
+}
