@@ -35,6 +35,7 @@ def main():
     eng.bind_adam(eng.new_actor_arena(), eng.new_actor_arena(), 0, eng.new_critic_arena(), eng.new_critic_arena(), 0)
     s = torch.randn(N, O, device=dev); s2 = torch.randn(N, O, device=dev)
     a = torch.rand(N, A, device=dev) * 2 - 1; r = torch.randn(N, device=dev); d = torch.rand(N, device=dev) < 1e-3
+    eng.set_precision(int(os.environ.get('SACB_PRECISION', '1')))
     eng.bind_buffer(s, a, r, s2, d)
     eng.set_buffer_state(0, N)
     eng.update(50)

@@ -5,25 +5,30 @@
 //   every operand tile is split in shared memory into hi = tf32(x) and lo = tf32(x - hi) and the tensor core
 //   accumulates a_lo*b_hi + a_hi*b_lo + a_hi*b_hi in fp32 (TMEM) -> fp32-level accuracy.
 //
-// Operand tiles live in shared memory in the canonical NO-SWIZZLE UMMA layouts (cute/atom/mma_traits_sm100.hpp,
-// make_umma_desc), addressed in 16-byte units ("chunks" of 4 tf32):
-//   K-major  (reduction contiguous in global memory):  chunk(m, kc) at (m/8)*SBO + kc*LBO + (m%8)*16,  LBO=128, SBO=8192
-//   MN-major (output contiguous in global memory):     chunk(k, mc) at (k/8)*LBO + mc*SBO + (k%8)*16,  SBO=128, LBO=(R/4)*128
-// so a 16-byte cp.async can drop every global chunk straight into place, and one tcgen05.mma (K = 8 tf32) reads
-// 2 K-major chunk columns (start += 256 B per k-step) or one MN-major k-group (start += LBO per k-step).
+// Operand tiles live in shared memory in canonical UMMA layouts (cute/atom/mma_traits_sm100.hpp, make_umma_desc),
+// built from 16-byte chunks (4 tf32) so that a 16-byte cp.async drops every global chunk straight into place:
+//   K-major  (reduction contiguous in global memory), SWIZZLE_NONE:
+//       byte(m, k) = (m/8)*SBO + (k/4)*LBO + (m%8)*16 + (k%4)*4            LBO = 128, SBO = 8192
+//       one tcgen05.mma (K = 8 tf32) reads two chunk columns: start += 256 B per k-step
+//   MN-major (output contiguous in global memory): tf32 supports ONLY SWIZZLE_128B_BASE32B here
+//   (cutlass/gemm/collective/builders/sm100_common.inl:92).  Atom = 4 k-rows x 32 outputs (128 B per k-row), the four
+//   32-byte groups of a row XOR-permuted by k%4 (Swizzle<2,5,2>):
+//       byte(m, k) = (m/32)*LBO + (k/4)*SBO + (k%4)*128 + 32*(((m%32)/8) ^ (k%4)) + (m%8)*4
+//       LBO = 512 (next 32-output atom), SBO = 512 * atoms (next group of 4 k);  start += 2*SBO per k-step
 // Accumulator: M = 64 rows occupy TMEM lanes (m%16) + 32*(m/16) (half of each sub-partition), 16 fp32 columns;
 // warp w reads rows 16w..16w+15 with tcgen05.ld.32x32b.x16 (lanes 0..15 hold one row each).
 #pragma once
 
 constexpr int kT5M = 64, kT5N = 16, kT5K = 256;                  // tile and K block
-constexpr int kT5AHi = 0, kT5ALo = 65536, kT5BHi = 131072, kT5BLo = 147456, kT5PipeBytes = 163840;
+constexpr int kT5AHi = 0, kT5ALo = 65536, kT5BHi = 131072, kT5BLo = 163840, kT5Epi = 196608, kT5PipeBytes = 198656;
 constexpr int kT5SboK = 8192, kT5LboK = 128;                     // K-major strides (bytes)
-constexpr int kT5SboMN = 128;                                    // MN-major: chunk stride; LBO = (R/4)*128
+constexpr int kT5LboMN = 512;                                    // MN-major: 32-output atom stride; SBO = 512 * atoms
 
-__device__ __forceinline__ unsigned long long t5_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
-    // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout_type=SWIZZLE_NONE
+__device__ __forceinline__ unsigned long long t5_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes, bool mn_major) {
+    // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout_type [61,64):
+    // SWIZZLE_NONE = 0 (K-major here), SWIZZLE_128B_BASE32B = 1 (MN-major tf32)
     return (unsigned long long)((smem_addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+           ((unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((mn_major ? 1ull : 0ull) << 61);
 }
 __device__ __forceinline__ unsigned t5_idesc(bool a_mn, bool b_mn) {
     // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format TF32 (2) [7,10) | b_format TF32 (2) [10,13) |
@@ -48,69 +53,98 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
                  "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" ::"r"(addr), "r"(parity) : "memory");
 }
 
-// chunk loader.  RC = K-major.  R = tile outputs (64 for A, 16 for B).  k_pad = roundup8(k_valid).
+// byte offset of element (o, k) of an operand tile with R outputs
 template <bool RC>
-__device__ __forceinline__ void t5_load(char* buf, const float* __restrict__ g, int ld, int R, int o0, int o_valid,
+__device__ __forceinline__ int t5_off(int o, int k, int R) {
+    if (RC) return (o >> 3) * kT5SboK + (k >> 2) * kT5LboK + (o & 7) * 16 + (k & 3) * 4;
+    const int sbo = ((R + 31) >> 5) * 512;
+    return (o >> 5) * kT5LboMN + (k >> 2) * sbo + (k & 3) * 128 + 32 * (((o & 31) >> 3) ^ (k & 3)) + (o & 7) * 4;
+}
+
+// chunk loader.  RC = K-major.  R = tile outputs (64 for A, 16 for B), compile-time so that all index math is shifts.
+// Work unit = 8 rows (K-major) / 8 k's (MN-major) x 4 chunks = one warp instruction: the 8 lanes that share a chunk
+// column write 8 consecutive 16-byte slots (conflict-free), the 4 chunk columns read 64 contiguous bytes per row.
+template <bool RC, int R>
+__device__ __forceinline__ void t5_load(char* buf, const float* __restrict__ g, int ld, int o0, int o_valid,
                                         int k0, int k_valid, int vec) {
     const int k_pad = (k_valid + 7) & ~7;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int l8 = lane & 7, c4 = lane >> 3;
     if (vec) {
-        if (RC) {       // unit = 8 rows x 4 chunks; units: (R/8) row groups x ceil(k_pad/16) chunk blocks
-            const int MG = R >> 3, CB = (k_pad + 15) >> 4;
-            for (int u = warp; u < MG * CB; u += kThreads / 32) {
-                const int mg = u % MG, kc = (u / MG) * 4 + c4;
-                const int row = mg * 8 + l8, kk = kc * 4;
+        if (RC) {
+            constexpr int MG = R >> 3;                     // 8 (A) or 2 (B) row groups
+            const int CB = (k_pad + 15) >> 4;              // chunk blocks of 4 chunks = 16 k
+            const int mg = warp & (MG - 1);
+            const int row = mg * 8 + l8;
+            const bool row_ok = row < o_valid;
+            const float* src_row = g + (size_t)(o0 + row) * ld + k0;
+            char* dst_row = buf + mg * kT5SboK + l8 * 16;
+#pragma unroll 4
+            for (int cb = warp / MG; cb < CB; cb += 8 / MG) {
+                const int kk = (cb * 4 + c4) * 4;
                 if (kk < k_pad) {
                     int nb = 0;
-                    if (row < o_valid && kk < k_valid) nb = min(4, k_valid - kk) * 4;
-                    const float* src = nb ? g + (size_t)(o0 + row) * ld + k0 + kk : g;
-                    cp_async16(buf + mg * kT5SboK + kc * kT5LboK + l8 * 16, src, nb);
+                    if (row_ok && kk < k_valid) nb = min(4, k_valid - kk) * 4;
+                    cp_async16(dst_row + (kk >> 2) * kT5LboK, nb ? src_row + kk : g, nb);
                 }
             }
-        } else {        // unit = 8 k's x 4 chunks; units: (k_pad/8) k groups x (R/16) chunk blocks
-            const int KG = k_pad >> 3, CB = R >> 4, lbo = (R >> 2) * 128;
-            for (int u = warp; u < KG * CB; u += kThreads / 32) {
-                const int kg = u % KG, mc = (u / KG) * 4 + c4;
-                const int kk = kg * 8 + l8, oo = mc * 4;
-                int nb = 0;
-                if (kk < k_valid && oo < o_valid) nb = min(4, o_valid - oo) * 4;
-                const float* src = nb ? g + (size_t)(k0 + kk) * ld + o0 + oo : g;
-                cp_async16(buf + kg * lbo + mc * kT5SboMN + l8 * 16, src, nb);
+        } else {
+            constexpr int CB = R >> 4;                     // 4 (A) or 1 (B) chunk blocks of 16 outputs
+            constexpr int SBO = ((R + 31) >> 5) * 512;
+            const int KG = k_pad >> 3;
+            const int cbi = warp & (CB - 1);
+            const int oo = (cbi * 4 + c4) * 4;
+            int nb_o = 0;
+            if (oo < o_valid) nb_o = min(4, o_valid - oo) * 4;
+            const float* src_col = g + (size_t)k0 * ld + o0 + oo;
+            // byte(o,k) = (o/32)*512 + (k/4)*SBO + (k%4)*128 + 32*(((o%32)/8) ^ (k%4)) + (o%8)*4
+            char* dst_col = buf + (oo >> 5) * kT5LboMN + (oo & 7) * 4;
+            const int og = (oo & 31) >> 3;
+#pragma unroll 4
+            for (int kg = warp / CB; kg < KG; kg += 8 / CB) {
+                const int kk = kg * 8 + l8;
+                const int nb = kk < k_valid ? nb_o : 0;
+                cp_async16(dst_col + (kk >> 2) * SBO + (kk & 3) * 128 + 32 * (og ^ (kk & 3)), nb ? src_col + (size_t)kk * ld : g, nb);
             }
         }
-    } else {            // element-wise path for unaligned operands; rows beyond o_valid stay stale (feed only unused outputs)
-        const int lbo = (R >> 2) * 128;
+    } else {            // element-wise path for unaligned operands; outputs beyond o_valid stay stale (feed only unused outputs)
         const int n_el = o_valid * k_pad;
         for (int e = threadIdx.x; e < n_el; e += kThreads) {
             int o, k;
             if (RC) { o = e / k_pad; k = e - o * k_pad; } else { k = e / o_valid; o = e - k * o_valid; }
-            char* dst = RC ? buf + (o >> 3) * kT5SboK + (k >> 2) * kT5LboK + (o & 7) * 16 + (k & 3) * 4
-                           : buf + (k >> 3) * lbo + (o >> 2) * kT5SboMN + (k & 7) * 16 + (o & 3) * 4;
+            char* dst = buf + t5_off<RC>(o, k, R);
             if (k < k_valid) cp_async4(dst, RC ? g + (size_t)(o0 + o) * ld + k0 + k : g + (size_t)(k0 + k) * ld + o0 + o);
             else *reinterpret_cast<float*>(dst) = 0.f;
         }
     }
 }
 
-// hi/lo split of everything the loader touched: x -> hi (in place), lo -> buf_lo (same layout).
-template <bool RC>
-__device__ __forceinline__ void t5_split(char* hi, char* lo, int R, int k_valid) {
+__device__ __forceinline__ void t5_split4(char* hi, char* lo, int off) {
+    float4 x = *reinterpret_cast<const float4*>(hi + off);
+    float4 h, l;
+    h.x = __uint_as_float(f2tf32(x.x)); l.x = __uint_as_float(f2tf32(x.x - h.x));
+    h.y = __uint_as_float(f2tf32(x.y)); l.y = __uint_as_float(f2tf32(x.y - h.y));
+    h.z = __uint_as_float(f2tf32(x.z)); l.z = __uint_as_float(f2tf32(x.z - h.z));
+    h.w = __uint_as_float(f2tf32(x.w)); l.w = __uint_as_float(f2tf32(x.w - h.w));
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+// hi/lo split of the region the loader touched: x -> hi (in place), lo -> buf_lo (same layout).
+template <bool RC, int R>
+__device__ __forceinline__ void t5_split(char* hi, char* lo, int k_valid) {
     const int k_pad = (k_valid + 7) & ~7;
-    int groups, per_group, gstride;                   // float4 units
-    if (RC) { groups = R >> 3; per_group = (k_pad >> 2) * 8; gstride = kT5SboK / 16; }
-    else { groups = k_pad >> 3; per_group = (R >> 2) * 8; gstride = (R >> 2) * 8; }
-    const int total = groups * per_group;
-    for (int i = threadIdx.x; i < total; i += kThreads) {
-        const int gi = i / per_group, off = (gi * gstride + (i - gi * per_group)) * 16;
-        float4 x = *reinterpret_cast<const float4*>(hi + off);
-        float4 h, l;
-        h.x = __uint_as_float(f2tf32(x.x)); l.x = __uint_as_float(f2tf32(x.x - h.x));
-        h.y = __uint_as_float(f2tf32(x.y)); l.y = __uint_as_float(f2tf32(x.y - h.y));
-        h.z = __uint_as_float(f2tf32(x.z)); l.z = __uint_as_float(f2tf32(x.z - h.z));
-        h.w = __uint_as_float(f2tf32(x.w)); l.w = __uint_as_float(f2tf32(x.w - h.w));
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = l;
+    if (RC) {           // per 8-row group: (k_pad/4) chunk columns x 128 B, contiguous
+        const int bytes = (k_pad >> 2) * 128;
+#pragma unroll
+        for (int mg = 0; mg < (R >> 3); ++mg) {
+#pragma unroll 2
+            for (int off = threadIdx.x * 16; off < bytes; off += kThreads * 16) t5_split4(hi, lo, mg * kT5SboK + off);
+        }
+    } else {            // contiguous: (k_pad/4) k-groups x atoms x 512 B
+        const int bytes = (k_pad >> 2) * ((R + 31) >> 5) * 512;
+#pragma unroll 4
+        for (int off = threadIdx.x * 16; off < bytes; off += kThreads * 16) t5_split4(hi, lo, off);
     }
 }
 
@@ -132,41 +166,58 @@ __device__ __forceinline__ void gemm_tile_t5(const Job& jb, int tile, char* pipe
     const float* __restrict__ Bg = jb.B + (size_t)z * jb.sB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     char* a_hi = pipe + kT5AHi; char* a_lo = pipe + kT5ALo; char* b_hi = pipe + kT5BHi; char* b_lo = pipe + kT5BLo;
+    float* s_bias = reinterpret_cast<float*>(pipe + kT5Epi);      // [16] bias, [16] w2, [16][17] post-product X slice
+    float* s_w2 = s_bias + 16;
+    float* s_x = s_w2 + 16;
 
     const unsigned idesc = t5_idesc(!A_RC, !B_RC);
-    const unsigned a_lbo = A_RC ? kT5LboK : (kT5M / 4) * 128, a_sbo = A_RC ? kT5SboK : kT5SboMN;
-    const unsigned b_lbo = B_RC ? kT5LboK : (kT5N / 4) * 128, b_sbo = B_RC ? kT5SboK : kT5SboMN;
-    const unsigned a_step = A_RC ? 256 : a_lbo, b_step = B_RC ? 256 : b_lbo;      // bytes per k-step of 8
+    constexpr unsigned a_lbo = A_RC ? kT5LboK : kT5LboMN, a_sbo = A_RC ? kT5SboK : 512u * ((kT5M + 31) / 32);
+    constexpr unsigned b_lbo = B_RC ? kT5LboK : kT5LboMN, b_sbo = B_RC ? kT5SboK : 512u * ((kT5N + 31) / 32);
+    constexpr unsigned a_step = A_RC ? 256u : 2u * a_sbo, b_step = B_RC ? 256u : 2u * b_sbo;      // bytes per k-step of 8
 
-    // epilogue operands for this thread's row (warps 0..3, lanes 0..15: row = 16*warp + lane)
+    // this thread's accumulator row (warps 0..3, lanes 0..15: row = 16*warp + lane)
     const int erow = 16 * warp + lane;
     const bool e_thread = warp < 4 && lane < 16;
     const int gi = i0 + erow;
     const bool row_ok = e_thread && gi < M;
+    const bool has_bias = jb.epi == E_BIAS || jb.epi == E_BIAS_RELU || jb.epi == E_BIAS_RELU_DOT;
+    const int J = jb.i1;
 
     for (int kb = 0; kb < K; kb += kT5K) {
         const int kv = min(kT5K, K - kb);
-        t5_load<A_RC>(a_hi, Ag, jb.lda, kT5M, i0, i_valid, kb, kv, jb.a_vec);
-        t5_load<B_RC>(b_hi, Bg, jb.ldb, kT5N, j0, j_valid, kb, kv, jb.b_vec);
+        t5_load<A_RC, kT5M>(a_hi, Ag, jb.lda, i0, i_valid, kb, kv, jb.a_vec);
+        t5_load<B_RC, kT5N>(b_hi, Bg, jb.ldb, j0, j_valid, kb, kv, jb.b_vec);
         cp_async_commit();
+        if (kb == 0) {
+            // epilogue operands of this tile's 16 columns -> shared memory (their L2 latency hides behind the operand loads)
+            const int t = threadIdx.x;
+            if (t < 16) s_bias[t] = (has_bias && j0 + t < N) ? __ldcg(jb.bias + (size_t)z * jb.sBias + j0 + t) : 0.f;
+            else if (t < 32) s_w2[t - 16] = (jb.epi == E_BIAS_RELU_DOT && j0 + t - 16 < N) ? __ldcg(jb.aux0 + (size_t)z * jb.sAux + j0 + t - 16) : 0.f;
+            if (J > 0 && t < 16 * J) {
+                const int j = t >> 4, c = t & 15;
+                const float* __restrict__ X = jb.aux1 + (size_t)z * jb.sAux;
+                s_x[j * 17 + c] = (j0 + c < N) ? __ldcg(jb.i3 ? X + (size_t)(j0 + c) * jb.i2 + j : X + (size_t)j * jb.i2 + j0 + c) : 0.f;
+            }
+        }
         cp_async_wait<0>();
         __syncthreads();
         TR(110);
-        t5_split<A_RC>(a_hi, a_lo, kT5M, kv);
-        t5_split<B_RC>(b_hi, b_lo, kT5N, kv);
+        t5_split<A_RC, kT5M>(a_hi, a_lo, kv);
+        t5_split<B_RC, kT5N>(b_hi, b_lo, kv);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the tensor core
         __syncthreads();
         TR(111);
         if (threadIdx.x == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+            unsigned long long dah = t5_desc(smem_u32(a_hi), a_lbo, a_sbo, !A_RC), dal = t5_desc(smem_u32(a_lo), a_lbo, a_sbo, !A_RC);
+            unsigned long long dbh = t5_desc(smem_u32(b_hi), b_lbo, b_sbo, !B_RC), dbl = t5_desc(smem_u32(b_lo), b_lbo, b_sbo, !B_RC);
             const int nk8 = (kv + 7) >> 3;
+#pragma unroll 4
             for (int k8 = 0; k8 < nk8; ++k8) {
-                const unsigned long long dah = t5_desc(ah + k8 * a_step, a_lbo, a_sbo), dal = t5_desc(al + k8 * a_step, a_lbo, a_sbo);
-                const unsigned long long dbh = t5_desc(bh + k8 * b_step, b_lbo, b_sbo), dbl = t5_desc(bl + k8 * b_step, b_lbo, b_sbo);
                 t5_mma(cx.tmem, dal, dbh, idesc, (kb | k8) ? 1u : 0u);
                 t5_mma(cx.tmem, dah, dbl, idesc, 1u);
                 t5_mma(cx.tmem, dah, dbh, idesc, 1u);
+                dah += a_step >> 4; dal += a_step >> 4; dbh += b_step >> 4; dbl += b_step >> 4;      // start-address field, 16-byte units
             }
             t5_commit(cx.mbar);                            // arrives when every MMA above has finished reading smem / writing TMEM
         }
@@ -178,6 +229,13 @@ __device__ __forceinline__ void gemm_tile_t5(const Job& jb, int tile, char* pipe
 
     // ---- epilogue: TMEM -> registers (one row of 16 columns per thread), fused bias / relu / mask / dots, store ----
     float v[16];
+    float4 mk[4];
+    const bool mask_vec = jb.epi == E_MASK && row_ok && j_valid == 16 && (jb.ldmask & 3) == 0 && (jb.sMask & 3) == 0;
+    if (mask_vec) {
+        const float4* mp = reinterpret_cast<const float4*>(jb.mask + (size_t)z * jb.sMask + (size_t)gi * jb.ldmask + j0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mk[q] = __ldcg(mp + q);
+    }
     if (warp < 4) {
         unsigned r[16];
         const unsigned taddr = cx.tmem + ((unsigned)(32 * warp) << 16);
@@ -190,19 +248,21 @@ __device__ __forceinline__ void gemm_tile_t5(const Job& jb, int tile, char* pipe
         for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
     }
     if (row_ok) {
-        const bool has_bias = jb.epi == E_BIAS || jb.epi == E_BIAS_RELU || jb.epi == E_BIAS_RELU_DOT;
         const bool relu = jb.epi == E_BIAS_RELU || jb.epi == E_BIAS_RELU_DOT;
         float dot = 0.f;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-            const int gj = j0 + c;
-            const bool ok = gj < N;
-            float x = v[c];
-            if (has_bias && ok) x += __ldcg(jb.bias + (size_t)z * jb.sBias + gj);
+            const bool ok = j0 + c < N;
+            float x = v[c] + s_bias[c];
             if (relu) x = fmaxf(x, 0.f);
-            if (jb.epi == E_MASK) x = (ok && __ldcg(jb.mask + (size_t)z * jb.sMask + (size_t)gi * jb.ldmask + gj) > 0.f) ? x : 0.f;
+            if (jb.epi == E_MASK) {
+                float m;
+                if (mask_vec) { const float4 q = mk[c >> 2]; m = (c & 3) == 0 ? q.x : (c & 3) == 1 ? q.y : (c & 3) == 2 ? q.z : q.w; }
+                else m = ok ? __ldcg(jb.mask + (size_t)z * jb.sMask + (size_t)gi * jb.ldmask + j0 + c) : 0.f;
+                x = m > 0.f ? x : 0.f;
+            }
             if (!ok) x = 0.f;
-            if (jb.epi == E_BIAS_RELU_DOT && ok) dot = fmaf(x, __ldcg(jb.aux0 + (size_t)z * jb.sAux + gj), dot);
+            dot = fmaf(x, s_w2[c], dot);
             v[c] = x;
         }
         float* __restrict__ crow = jb.C + (size_t)z * jb.sC + (size_t)gi * jb.ldc + j0;
@@ -214,14 +274,11 @@ __device__ __forceinline__ void gemm_tile_t5(const Job& jb, int tile, char* pipe
             for (int c = 0; c < 16; ++c) if (c < j_valid) crow[c] = v[c];
         }
         if (jb.epi == E_BIAS_RELU_DOT) jb.out0[((size_t)z * tn + tj) * jb.i0 + gi] = dot;
-        const int J = jb.i1;
         if (J > 0) {     // post-product: P[j] = sum_c v[c] * X[j][c]  (heads off h2, d pi off dh1), see gemm_tile
-            const float* __restrict__ X = jb.aux1 + (size_t)z * jb.sAux;
             for (int j = 0; j < J; ++j) {
                 float p = 0.f;
 #pragma unroll
-                for (int c = 0; c < 16; ++c)
-                    if (j0 + c < N) p = fmaf(v[c], __ldcg(jb.i3 ? X + (size_t)(j0 + c) * jb.i2 + j : X + (size_t)j * jb.i2 + j0 + c), p);
+                for (int c = 0; c < 16; ++c) p = fmaf(v[c], s_x[j * 17 + c], p);
                 jb.out1[(((size_t)z * tn + tj) * J + j) * jb.i0 + gi] = p;
             }
         }
