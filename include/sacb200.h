@@ -153,6 +153,17 @@ int sacb_comm_unique_id(const char* nccl_lib_path, uint8_t id_out[128]);
 int sacb_comm_init(sacb_handle h, const char* nccl_lib_path, const uint8_t id[128], int32_t rank, int32_t world);
 int sacb_sync_params(sacb_handle h, uintptr_t stream);
 
+/* Peer mode: the gradient averaging of sac/mpi.py:77-85 fused INTO the update kernel.  Every rank maps every other rank's
+ * engine workspace (CUDA IPC, same node, NVLink peers); in the Adam phases one thread per peer publishes "my gradient
+ * of update t is complete" (system-scope release store into the peer's flag word), every CTA waits for all ranks' flags
+ * (system-scope acquire) and then sums the ranks' gradient arenas over NVLink in fixed rank order while it applies
+ * Adam.  No NCCL call and no extra kernel launch per update: a data-parallel burst stays one persistent launch and the
+ * replicas stay bit-identical.  sacb_peer_export: 64-byte cudaIpcMemHandle of this rank's workspace (+ its length, which
+ * must agree on all ranks).  sacb_peer_bind: the handles of all ranks, [world][64] bytes in rank order (world <= 8).
+ * sacb_comm_init may still be used next to it for sacb_sync_params. */
+int sacb_peer_export(sacb_handle h, uint8_t handle_out[64], int64_t* ws_floats);
+int sacb_peer_bind(sacb_handle h, const uint8_t* handles, int32_t rank, int32_t world);
+
 /* Test / debug: copy an internal f32 array to HOST memory (synchronous).  Names: "backup","q1","q2","q1_target",
  * "q2_target","a2","logp_next","pi","logp_pi","q1_pi","q2_pi","grad_actor","grad_critic","loss_q_parts", ...
  * Returns the number of floats written via *n_out. */

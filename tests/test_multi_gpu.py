@@ -35,7 +35,7 @@ def _rank_data(rank):
     return arrays, idx, eps
 
 
-def _worker(rank, world, port, flags, q):
+def _worker(rank, world, port, flags, comm, q):
     try:
         os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         import torch.distributed as dist
@@ -55,6 +55,8 @@ def _worker(rank, world, port, flags, q):
         eng.bind_adam(eng.new_actor_arena(), eng.new_actor_arena(), 0, eng.new_critic_arena(), eng.new_critic_arena(), 0)
         eng.comm_init_from_torch()
         eng.sync_params()                                                             # ... sync_params makes them rank 0's
+        if comm == "peer":
+            eng.peer_init_from_torch()                                                # fused in-kernel NVLink exchange
         arrays, idx, eps = _rank_data(rank)
         dev = eng.tdev()
         t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in arrays.items()}
@@ -114,8 +116,10 @@ def _flatten(eng_layout_views, params):
     return np.concatenate([np.asarray(params[k], np.float64).reshape(-1) for k in eng_layout_views])
 
 
-@pytest.mark.parametrize("sync_actor", [True, False])
-def test_two_rank_nccl_update_matches_oracle(sync_actor):
+@pytest.mark.parametrize("sync_actor,comm", [(True, "nccl"), (False, "nccl"), (True, "peer")])
+def test_two_rank_update_matches_oracle(sync_actor, comm):
+    """comm = "nccl": ncclAllReduce between the backward and Adam launches; comm = "peer": the exchange fused into the
+    persistent kernel (system-scope flags + NVLink loads of the peers' gradient arenas, one launch per burst)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from torch_actor_critic_b200 import _lib
@@ -126,7 +130,7 @@ def test_two_rank_nccl_update_matches_oracle(sync_actor):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, flags, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, flags, comm, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in procs], key=lambda x: x[0])

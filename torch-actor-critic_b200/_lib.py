@@ -66,6 +66,8 @@ _PROTOS = {
     "sacb_comm_unique_id": (C.c_int, [C.c_char_p, _P]),
     "sacb_comm_init": (C.c_int, [_P, C.c_char_p, _P, _I32, _I32]),
     "sacb_sync_params": (C.c_int, [_P, _U]),
+    "sacb_peer_export": (C.c_int, [_P, _P, C.POINTER(_I64)]),
+    "sacb_peer_bind": (C.c_int, [_P, _P, _I32, _I32]),
     "sacb_debug_read": (C.c_int, [_P, C.c_char_p, _P, _I64, C.POINTER(_I64)]),
     "sacb_debug_profile": (C.c_int, [_P, _I32, _P, _I64, C.POINTER(_I32), C.POINTER(_I32), _U]),
     "sacb_launch_count": (_I64, [_P]),

@@ -131,6 +131,10 @@ struct sacb_engine {
     // comm
     nccl_comm_t comm = nullptr;
     int rank = 0, world = 1;
+    // peer mode: in-kernel NVLink gradient exchange (workspaces mapped across ranks with CUDA IPC)
+    int peer_mode = 0;
+    float* peer_ws[kMaxPeers] = {nullptr};
+    float* peer_flags = nullptr;
 };
 
 static void compute_layout(const sacb_config& c, sacb_layout_info& L) {
@@ -358,6 +362,11 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
         ra.adam_coef[k][3] = (float)std::sqrt(1.0 - std::pow(c.beta2, tq));
     }
     ra.tf32x3 = e->tf32x3;
+    ra.peer_world = e->peer_mode ? e->world : 1;
+    ra.peer_rank = e->rank;
+    for (int r = 0; r < kMaxPeers; ++r) ra.peer_ws[r] = e->peer_ws[r];
+    ra.peer_off_flags = e->peer_flags - e->ws;
+    ra.epoch_q = e->step_q; ra.epoch_pi = e->step_pi;
     ra.grad_div = (float)e->world;
     ra.flags = c.flags;
     ra.O = c.obs_dim; ra.A = c.act_dim; ra.H1 = c.hidden1; ra.H2 = c.hidden2; ra.B = c.batch_size;
@@ -458,6 +467,7 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     want(e->hpart, tn16_H2 * 2 * A * B); want(e->dpart, 2LL * tn16_H1 * A * B);
     want(e->lparts_q, 4LL * e->row_tiles); want(e->lparts_pi, 4LL * e->row_tiles); want(e->loss_scalar, 4);
     want(e->ga, e->lay.actor_floats); want(e->gc, e->lay.critic_floats);
+    want(e->peer_flags, 2 * kMaxPeers * 2);          // [2][kMaxPeers] u64 exchange epochs, written by the peers
     e->ws_floats = off;
     CU(cudaMalloc(&e->ws, off * sizeof(float)));
     CU(cudaMemset(e->ws, 0, off * sizeof(float)));
@@ -478,6 +488,8 @@ int sacb_destroy(sacb_handle e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (e->peer_mode && e->peer_ws[r] && r != e->rank) cudaIpcCloseMemHandle(e->peer_ws[r]);
     cudaFree(e->ws); cudaFree(e->idx_buf); cudaFree(e->perm_buf); cudaFree(e->eps_buf); cudaFree(e->barrier);
     cudaFree(e->d_jobs); cudaFree(e->d_phases);
     if (e->stage) cudaFreeHost(e->stage);
@@ -699,7 +711,9 @@ int sacb_update(sacb_handle e, int32_t n_updates, const int64_t* idx_in, const f
     ra.eps1 = eps; ra.eps2 = eps + (size_t)B * A; ra.eps_stride = 2LL * B * A;
     ra.loss_q_out = loss_q; ra.loss_pi_out = loss_pi;
     ra.fuse_polyak = 1; ra.pass_mask = 3; ra.k_total = n_updates;
-    if (e->world <= 1) {
+    if (e->world <= 1 || e->peer_mode) {
+        // single GPU, or peer mode: the gradient exchange is fused into the Adam phases (NVLink loads from the peers'
+        // arenas), so a data-parallel burst is still ONE persistent launch
         if (int r = run_phases(e, ra, e->p_update.begin, e->p_update.end, 0, n_updates, st)) return r;
     } else {
         const bool sync_actor = !(e->cfg.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC);
@@ -755,7 +769,7 @@ int sacb_update_critic(sacb_handle e, const float* eps_in, float* loss_q, uintpt
     fill_args(e, ra);
     ra.eps1 = eps; ra.eps2 = nullptr; ra.eps_stride = 0; ra.pass_mask = 1; ra.fuse_polyak = 0;
     ra.loss_q_out = loss_q;
-    if (e->world <= 1) {
+    if (e->world <= 1 || e->peer_mode) {
         if (int r = run_phases(e, ra, e->ph_crit_begin, e->ph_crit_adam + 1, 0, 1, st)) return r;
     } else {
         if (int r = run_phases(e, ra, e->ph_crit_begin, e->ph_crit_adam, 0, 1, st)) return r;
@@ -779,8 +793,10 @@ int sacb_update_policy(sacb_handle e, const float* eps_in, float* loss_pi, uintp
     ra.eps1 = nullptr; ra.eps2 = eps; ra.eps_stride = 0; ra.pass_mask = 2; ra.fuse_polyak = 0;
     ra.loss_pi_out = loss_pi;
     const int adam = e->p_policy.end - 1;
-    const bool sync_actor = e->world > 1 && !(e->cfg.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC);
-    if (!sync_actor) {
+    const bool sync_actor = e->world > 1 && !e->peer_mode && !(e->cfg.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC);
+    if (e->peer_mode) {
+        if (int r = run_phases(e, ra, e->p_policy.begin, e->p_policy.end, 0, 1, st)) return r;
+    } else if (!sync_actor) {
         ra.grad_div = 1.f;
         if (int r = run_phases(e, ra, e->p_policy.begin, e->p_policy.end, 0, 1, st)) return r;
     } else {
@@ -880,9 +896,40 @@ int sacb_comm_init(sacb_handle e, const char* lib, const uint8_t id_in[128], int
     return 0;
 }
 
+int sacb_peer_export(sacb_handle e, uint8_t handle_out[64], int64_t* ws_floats) {
+    if (!e || !handle_out) return fail(SACB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    cudaIpcMemHandle_t hnd;
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU(cudaIpcGetMemHandle(&hnd, e->ws));
+    memcpy(handle_out, &hnd, 64);
+    if (ws_floats) *ws_floats = (int64_t)e->ws_floats;
+    return 0;
+}
+
+int sacb_peer_bind(sacb_handle e, const uint8_t* handles, int32_t rank, int32_t world) {
+    if (!e || !handles) return fail(SACB_ERR_INVALID, "null argument");
+    if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world) return fail(SACB_ERR_INVALID, "peer mode needs 2..%d ranks", kMaxPeers);
+    if (e->cfg.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC)
+        return fail(SACB_ERR_INVALID, "peer mode relies on both exchanges per update to interlock the ranks; use the NCCL communicator with SACB_FLAG_NO_ACTOR_GRAD_SYNC");
+    CU(cudaSetDevice(e->cfg.device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { e->peer_ws[r] = e->ws; continue; }
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, handles + 64 * r, 64);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        e->peer_ws[r] = (float*)p;
+    }
+    e->rank = rank; e->world = world; e->peer_mode = 1;
+    e->dirty = true;
+    return 0;
+}
+
 int sacb_sync_params(sacb_handle e, uintptr_t stream) {
     if (!e) return fail(SACB_ERR_INVALID, "null handle");
     if (e->world <= 1) return 0;                      // sync_params early return, sac/mpi.py:94-95
+    if (!e->comm) return fail(SACB_ERR_STATE, "sacb_sync_params needs the NCCL communicator (sacb_comm_init)");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(e->cfg.device));
     if (e->pa) NC(g_nccl.Broadcast(e->pa, e->pa, (size_t)e->lay.actor_floats, kNcclFloat, 0, e->comm, st));

@@ -40,6 +40,7 @@ static void build_programs(sacb_engine* e) {
     const int row_tiles = e->row_tiles;
     const bool fuse_heads = 2 * A <= 16, fuse_dpi = A <= 16;
     const int tnH1 = (H1 + e->tile_n - 1) / e->tile_n;
+    const bool actor_sync = !(c.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC);
 
     // ---- job factories -------------------------------------------------------------------------------------------
     auto actor_l0 = [&](int dyn, int b_static) {
@@ -89,6 +90,11 @@ static void build_programs(sacb_engine* e) {
         if (critic) { j.C = PC; j.A = GC; j.out0 = e->mc; j.out1 = e->vc; j.out2 = PT; j.K = (int)L.critic_floats; j.i0 = 1; }
         else { j.C = PA; j.A = GA; j.out0 = e->ma; j.out1 = e->va; j.out2 = nullptr; j.K = (int)L.actor_floats; j.i0 = 0; }
         j.ntiles = (j.K + kThreads * 4 - 1) / (kThreads * 4);
+        j.i2 = 1;                                  // gradient comes from the data-parallel exchange when one is active
+        return j; };
+    auto peer_signal = [&](bool critic) {
+        Job j = Builder::zero();
+        j.type = J_PEER_SIGNAL; j.i0 = critic ? 1 : 0; j.ntiles = 1;
         return j; };
 
     // actor trunk + heads + tanh-Gaussian rows; `with_critic` interleaves the online critic's forward (update_critic)
@@ -152,7 +158,8 @@ static void build_programs(sacb_engine* e) {
             b.add(j);
         }
         int adam_phase = b.phase();
-        b.add(adam(false));
+        if (e->peer_mode && actor_sync) b.add(peer_signal(false));
+        { Job j = adam(false); if (!actor_sync) j.i2 = 0; b.add(j); }
         return adam_phase;
     };
 
@@ -195,7 +202,7 @@ static void build_programs(sacb_engine* e) {
         b.add(j);
     }
     e->ph_crit_adam = (int)e->phases.size();
-    b.phase(); b.add(adam(true));                                                            // Adam(critic) [+ Polyak]
+    b.phase(); if (e->peer_mode) b.add(peer_signal(true)); b.add(adam(true));                // Adam(critic) [+ Polyak]
     e->ph_pi_begin = (int)e->phases.size();
     e->ph_pi_adam = policy_tail(false);
     b.add(gather(1));                                      // prefetch the next update's batch (staging tiles are idle here)

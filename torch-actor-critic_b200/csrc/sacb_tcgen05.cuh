@@ -20,6 +20,7 @@
 #pragma once
 
 constexpr int kT5M = 64, kT5N = 16, kT5K = 256;                  // tile and K block
+constexpr int kT5Acc = 8, kT5TmemCols = kT5Acc * kT5N;           // independent TMEM accumulators (128 columns)
 constexpr int kT5AHi = 0, kT5ALo = 65536, kT5BHi = 131072, kT5BLo = 163840, kT5Epi = 196608, kT5PipeBytes = 198656;
 constexpr int kT5SboK = 8192, kT5LboK = 128;                     // K-major strides (bytes)
 constexpr int kT5LboMN = 512;                                    // MN-major: 32-output atom stride; SBO = 512 * atoms
@@ -121,11 +122,13 @@ __device__ __forceinline__ void t5_load(char* buf, const float* __restrict__ g, 
 
 __device__ __forceinline__ void t5_split4(char* hi, char* lo, int off) {
     float4 x = *reinterpret_cast<const float4*>(hi + off);
+    // hi = x with the 13 low mantissa bits cleared (exactly a tf32 value, whatever rounding the tensor core applies);
+    // lo = x - hi is exact in fp32 and |lo| < 2^-10 |x|, so its own tf32 truncation costs < 2^-20 |x|.
     float4 h, l;
-    h.x = __uint_as_float(f2tf32(x.x)); l.x = __uint_as_float(f2tf32(x.x - h.x));
-    h.y = __uint_as_float(f2tf32(x.y)); l.y = __uint_as_float(f2tf32(x.y - h.y));
-    h.z = __uint_as_float(f2tf32(x.z)); l.z = __uint_as_float(f2tf32(x.z - h.z));
-    h.w = __uint_as_float(f2tf32(x.w)); l.w = __uint_as_float(f2tf32(x.w - h.w));
+    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
 }
@@ -212,11 +215,14 @@ __device__ __forceinline__ void gemm_tile_t5(const Job& jb, int tile, char* pipe
             unsigned long long dah = t5_desc(smem_u32(a_hi), a_lbo, a_sbo, !A_RC), dal = t5_desc(smem_u32(a_lo), a_lbo, a_sbo, !A_RC);
             unsigned long long dbh = t5_desc(smem_u32(b_hi), b_lbo, b_sbo, !B_RC), dbl = t5_desc(smem_u32(b_lo), b_lbo, b_sbo, !B_RC);
             const int nk8 = (kv + 7) >> 3;
+            // kT5Acc independent accumulators (k-step mod kT5Acc): MMAs into the same TMEM tile serialise on its ~64-cycle
+            // latency, and with N = 16 each MMA is only ~8 cycles of math
 #pragma unroll 4
             for (int k8 = 0; k8 < nk8; ++k8) {
-                t5_mma(cx.tmem, dal, dbh, idesc, (kb | k8) ? 1u : 0u);
-                t5_mma(cx.tmem, dah, dbl, idesc, 1u);
-                t5_mma(cx.tmem, dah, dbh, idesc, 1u);
+                const unsigned d = cx.tmem + (unsigned)((k8 & (kT5Acc - 1)) * kT5N);
+                t5_mma(d, dal, dbh, idesc, (kb == 0 && k8 < kT5Acc) ? 0u : 1u);
+                t5_mma(d, dah, dbl, idesc, 1u);
+                t5_mma(d, dah, dbh, idesc, 1u);
                 dah += a_step >> 4; dal += a_step >> 4; dbh += b_step >> 4; dbl += b_step >> 4;      // start-address field, 16-byte units
             }
             t5_commit(cx.mbar);                            // arrives when every MMA above has finished reading smem / writing TMEM
@@ -237,15 +243,20 @@ __device__ __forceinline__ void gemm_tile_t5(const Job& jb, int tile, char* pipe
         for (int q = 0; q < 4; ++q) mk[q] = __ldcg(mp + q);
     }
     if (warp < 4) {
-        unsigned r[16];
-        const unsigned taddr = cx.tmem + ((unsigned)(32 * warp) << 16);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                     : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int nacc = min(kT5Acc, (min(kT5K, K) + 7) >> 3);        // accumulators the first K block initialised
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
+        for (int c = 0; c < 16; ++c) v[c] = 0.f;
+        for (int a = 0; a < nacc; ++a) {                               // fixed summation order -> deterministic
+            unsigned r[16];
+            const unsigned taddr = cx.tmem + ((unsigned)(32 * warp) << 16) + (unsigned)(a * kT5N);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] += __uint_as_float(r[c]);
+        }
     }
     if (row_ok) {
         const bool relu = jb.epi == E_BIAS_RELU || jb.epi == E_BIAS_RELU_DOT;

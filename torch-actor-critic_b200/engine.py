@@ -301,6 +301,26 @@ class Engine:
         check(self._lib.sacb_comm_init(self._h, pb, uid, rank, world))
         self.world = world
 
+    def peer_init_from_torch(self):
+        """Fused in-kernel NVLink gradient exchange (include/sacb200.h, sacb_peer_bind): map every rank's engine workspace
+        into every other rank via CUDA IPC; handles travel over the default torch.distributed group."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        rank, world = dist.get_rank(), dist.get_world_size()
+        hnd = (C.c_uint8 * 64)()
+        n = C.c_int64()
+        check(self._lib.sacb_peer_export(self._h, hnd, C.byref(n)))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (bytes(hnd), n.value))
+        if len({g[1] for g in gathered}) != 1:
+            raise RuntimeError("peer mode needs identical engine configurations on all ranks")
+        blob = b"".join(g[0] for g in gathered)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(self._lib.sacb_peer_bind(self._h, buf, rank, world))
+        self.world = world
+        dist.barrier()
+
     def sync_params(self):
         check(self._lib.sacb_sync_params(self._h, self._stream()))
 

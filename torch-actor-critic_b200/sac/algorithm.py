@@ -145,7 +145,10 @@ class SAC(object):
             ent = dict(engine=eng, target=None, pi=None, q=None)
             eng.bind_params(actor=actor.arena, critic=critic.arena, target=None)
             if num_procs() > 1:
-                eng.comm_init_from_torch()
+                eng.comm_init_from_torch()                 # NCCL communicator (parameter broadcast, fallback exchange)
+                import os
+                if os.environ.get("SACB_COMM", "peer") == "peer":
+                    eng.peer_init_from_torch()             # gradient exchange fused into the update kernel (NVLink)
             self._engines[key] = ent
         eng = ent["engine"]
         for name, val in (("alpha", self.alpha), ("gamma", self.gamma), ("polyak", self.polyak), ("reward_scale", self.reward_scale)):
