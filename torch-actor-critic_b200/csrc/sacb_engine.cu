@@ -387,7 +387,8 @@ static int run_phases(sacb_engine* e, RunArgs ra, int pb, int pe, int kb, int ke
                 ra.phase_begin = p; ra.phase_end = p + 1; ra.k_begin = k; ra.k_end = k + 1; ra.use_barrier = 0;
                 int nt = e->phases[p].ntiles;
                 int grid = nt < 1 ? 1 : nt;
-                sac_phase_kernel<<<grid, kThreads, e->tf32x3 == 2 ? kSmemBytesT5 : kSmemBytes, st>>>(ra);
+                if (e->tf32x3 == 2) sac_phase_kernel<true><<<grid, kThreads, kSmemBytesT5, st>>>(ra);
+                else sac_phase_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(ra);
                 CU(cudaGetLastError());
                 e->launches++;
             }
@@ -396,8 +397,10 @@ static int run_phases(sacb_engine* e, RunArgs ra, int pb, int pe, int kb, int ke
     ra.phase_begin = pb; ra.phase_end = pe; ra.k_begin = kb; ra.k_end = ke; ra.use_barrier = 1;
     CU(cudaMemsetAsync(e->barrier, 0, sizeof(unsigned long long), st));
     void* args[] = {&ra};
-    CU(cudaLaunchCooperativeKernel((void*)sac_phase_kernel, dim3(e->grid_coop), dim3(kThreads), args,
-                                   e->tf32x3 == 2 ? kSmemBytesT5 : kSmemBytes, st));
+    if (e->tf32x3 == 2)
+        CU(cudaLaunchCooperativeKernel((void*)sac_phase_kernel<true>, dim3(e->grid_coop), dim3(kThreads), args, kSmemBytesT5, st));
+    else
+        CU(cudaLaunchCooperativeKernel((void*)sac_phase_kernel<false>, dim3(e->grid_coop), dim3(kThreads), args, kSmemBytes, st));
     e->launches++;
     return 0;
 }
@@ -435,15 +438,18 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, cfg->device));
     e->num_sms = prop.multiProcessorCount;
-    CU(cudaFuncSetAttribute(sac_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesT5));
+    CU(cudaFuncSetAttribute(sac_phase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CU(cudaFuncSetAttribute(sac_phase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesT5));
     CU(cudaFuncSetAttribute(draw_indices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * (int)sizeof(long long)));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sac_phase_kernel, kThreads, kSmemBytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sac_phase_kernel<false>, kThreads, kSmemBytes));
     if (occ < 1) { delete e; return fail(SACB_ERR_CUDA, "sac_phase_kernel does not fit on an SM"); }
     if (occ > 2) occ = 2;
+    occ = 1;    // one CTA per SM measured faster than two (8742 vs 8267 updates/s at C1): half the barrier participants
+    if (const char* o = getenv("SACB_OCC")) { if (atoi(o) == 2) occ = 2; }      // experiment knob
     e->grid_std = occ * e->num_sms;
     int occ5 = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ5, sac_phase_kernel, kThreads, kSmemBytesT5));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ5, sac_phase_kernel<true>, kThreads, kSmemBytesT5));
     e->grid_t5 = (occ5 < 1 ? 0 : 1) * e->num_sms;
     e->grid_coop = e->grid_std;
 
