@@ -171,7 +171,7 @@ def run_gpu(args):
 
     arrays = synth_buffer(rank)
     torch.manual_seed(0)
-    actor = Actor(O, A, H, act_limit=1.0, device=local)
+    actor = Actor(O, A, H, act_limit=1.0 if args.workload == 'c1' else 0.4, device=local)
     critic = DoubleCritic(O, A, H, device=local)
     target = deepcopy(critic)
     sync_params(actor); sync_params(critic); sync_params(target)
@@ -288,6 +288,18 @@ def run_gpu(args):
     print(json.dumps(line), flush=True)
 
 
+def set_workload(name):
+    global O, A, H, B, N_BUF, P_ACTOR, P_CRITIC, BYTES_PER_UPDATE, FLOPS_PER_UPDATE, WORKLOAD
+    if name == "c2":
+        O, A, H, B, N_BUF = 376, 17, [512, 512], 1024, 200_000
+        P_ACTOR, P_CRITIC = 473_122, 929_794
+        BYTES_PER_UPDATE = B * (2 * O + A + 2) * 4 + 28 * (P_ACTOR + P_CRITIC) + 12 * P_CRITIC
+        a_f = O * 512 + 512 * 512 + 2 * 512 * A
+        c_f = (O + A) * 512 + 512 * 512 + 512
+        FLOPS_PER_UPDATE = 2 * B * (3 * a_f + 10 * c_f + 3 * 512 * 512 + 2 * 512 + 2 * 512 * A)
+        WORKLOAD = "Humanoid-shaped synthetic replay (obs=376, act=17, 2e5 transitions), MLP 512x512, batch=1024, fp32 storage"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,10 +308,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", type=int, default=0, help="profiling only: 1 = one kernel launch per phase")
     ap.add_argument("--no-cpu", action="store_true", help="profiling only: skip the cpu_baseline leg")
-    ap.add_argument("--precision", type=int, default=1, help="1 = tensor-core 3xTF32 GEMMs (default), 0 = fp32 FFMA")
+    ap.add_argument("--precision", type=int, default=1, help="1 = mma.sync 3xTF32 GEMMs (default), 0 = fp32 FFMA, 2 = tcgen05 3xTF32")
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2"],
+                    help="c1 = BASELINE metric workload (default); c2 = Humanoid-shaped (obs=376, act=17, MLP 512x512, batch=1024), "
+                         "fp32 storage -- side measurement only, not the bench line the driver reads")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    set_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:

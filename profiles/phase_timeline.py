@@ -14,8 +14,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-PHASES = ["gather(first only)", "A.L0+C.L0", "A.L1(+heads)+C.L1q1", "rows_heads+C.L1q2", "T.L0", "T.L1", "row_backup",
-          "C.dh1+db1+dW2", "C.dW1+dW0+db0+lossq", "adam_c+polyak", "Cpi.L0", "Cpi.L1", "row_pi", "Cpi.dh1(+dpi)", "row_ghead",
+PHASES = ["gather(first only)", "A.L0+C.L0q1", "A.L1(+heads)+C.L1q1+C.L0q2", "rows_heads+C.L1q2", "T.L0", "T.L1", "row_backup",
+          "C.dh1+db1+dW2+lossq", "C.dW1+dW0+db0", "adam_c+polyak", "Cpi.L0", "Cpi.L1", "row_pi", "Cpi.dh1(+dpi)", "row_ghead",
           "A.dWh+dh2", "A.dW1+dh1", "A.dW0+losspi", "adam_a+gather(k+1)"]
 
 

@@ -207,10 +207,11 @@ struct Builder {
         if (nz > 2) { fprintf(stderr, "sacb: nz > 2 unsupported\n"); abort(); }
         return j;
     }
-    Job colsum(const float* X, int ldx, long long sX, const float* w, long long sW, float* out, long long sOut, int M, int N, int nz) {
+    Job colsum(const float* X, int ldx, long long sX, const float* w, long long sW, float* out, long long sOut, int M, int N, int nz,
+               int width = 32) {
         Job j = zero();
         j.type = J_COLSUM; j.A = X; j.lda = ldx; j.sA = sX; j.aux0 = w; j.sAux = sW; j.C = out; j.sC = sOut;
-        j.M = M; j.N = N; j.nz = nz; j.ntiles = ((N + 31) / 32) * nz;
+        j.M = M; j.N = N; j.nz = nz; j.i0 = width; j.ntiles = ((N + width - 1) / width) * nz;
         return j;
     }
 };

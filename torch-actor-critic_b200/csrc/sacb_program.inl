@@ -62,9 +62,11 @@ static void build_programs(sacb_engine* e) {
         j.out0 = e->x2; j.out1 = e->logp; j.out2 = e->xp; j.out3 = e->logp + B; j.ldc = ldx; j.i0 = O;
         if (fuse_heads) { j.i1 = e->tnH2; j.B = e->hpart; j.i2 = B; j.bias = PA + L.actor_b_mu; }
         j.ntiles = (B + 7) / 8; return j; };
-    auto critic_l0 = [&](float* P, const float* X, float* H, int dyn, int b_static) {
-        Job j = b.gemm(G_FWD, E_BIAS_RELU, X, ldx, 0, P + L.critic_w0[0], OA, 0, H, 2 * H1, 0, B, 2 * H1, OA, 1, dyn);
-        j.bias = P + L.critic_b0[0]; j.b_static = b_static; return j; };
+    // twin layer 0 as ONE [2*H1, O+A] GEMM, or (half = 0 / 1) only the q1 / q2 half of its output columns
+    auto critic_l0 = [&](float* P, const float* X, float* H, int dyn, int b_static, int half = -1) {
+        const int c0 = half < 0 ? 0 : half * H1, nc = half < 0 ? 2 * H1 : H1;
+        Job j = b.gemm(G_FWD, E_BIAS_RELU, X, ldx, 0, P + L.critic_w0[0] + (size_t)c0 * OA, OA, 0, H + c0, 2 * H1, 0, B, nc, OA, 1, dyn);
+        j.bias = P + L.critic_b0[0] + c0; j.b_static = b_static; return j; };
     // z0 .. z0+nz-1 of the twin layer 1 (with the Q-dot epilogue)
     auto critic_l1 = [&](float* P, const float* Hin, float* Hout, float* part, int dyn, int z0, int nz) {
         Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, Hin + (size_t)z0 * H1, 2 * H1, H1, P + L.critic_w1[z0], H1, sW1,
@@ -99,8 +101,11 @@ static void build_programs(sacb_engine* e) {
 
     // actor trunk + heads + tanh-Gaussian rows; `with_critic` interleaves the online critic's forward (update_critic)
     auto actor_forward = [&](int dyn, bool with_critic, int l0_static) {
-        b.phase(); b.add(actor_l0(dyn, l0_static)); if (with_critic) b.add(critic_l0(PC, e->xs, e->ch1, 0, 1));
-        b.phase(); b.add(actor_l1(dyn)); if (with_critic) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 1));
+        // tile budget: one round = one tile per SM.  A.L0 + C.L0[q1] (e.g. 64 + 64 tiles) now, C.L0[q2] rides as the
+        // cheap second tile of the next phase (its consumer C.L1[q2] runs one phase later anyway)
+        b.phase(); b.add(actor_l0(dyn, l0_static)); if (with_critic) b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 0));
+        b.phase(); b.add(actor_l1(dyn));
+        if (with_critic) { b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 1)); b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 1)); }
         if (!fuse_heads) { b.phase(); b.add(actor_heads(dyn)); if (with_critic) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1)); }
         b.phase(); b.add(row_heads(dyn));
         if (with_critic && fuse_heads) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1));
@@ -185,21 +190,22 @@ static void build_programs(sacb_engine* e) {
         j.out2 = e->logp; j.aux2 = e->rd; j.aux3 = e->rd + B; j.ntiles = row_tiles;
         b.add(j);
     }
-    {   // dh1 first (layer-0 gradients need it), bias / head-weight gradients ride along
+    {   // dh1 first (layer-0 gradients need it); the light jobs (bias / head-weight gradients as 64-wide column sums,
+        // loss reduction) fit on the SMs the GEMM tiles leave idle: 128 + 8 + 8 + 1 = 145 tiles at C1
         b.phase();
         b.add(critic_dx1(false));
-        b.add(b.colsum(e->dh2, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, B, 2 * H2, 1));
-        b.add(b.colsum(e->ch2, 2 * H2, H2, e->qbuf + 5 * (size_t)B, B, GC + L.critic_w2[0], H2, B, H2, 2));
-    }
-    {   // weight gradients of both layers, loss
-        b.phase();
-        b.add(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2));
-        b.add(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1));
-        b.add(b.colsum(e->dh1, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, B, 2 * H1, 1));
+        b.add(b.colsum(e->dh2, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, B, 2 * H2, 1, 64));
+        b.add(b.colsum(e->ch2, 2 * H2, H2, e->qbuf + 5 * (size_t)B, B, GC + L.critic_w2[0], H2, B, H2, 2, 64));
         Job j = Builder::zero();
         j.type = J_REDUCE_Q; j.A = e->lparts_q; j.i0 = row_tiles; j.out0 = e->loss_scalar; j.out1 = GC + L.critic_b2[0];
         j.out2 = GC + L.critic_b2[1]; j.ntiles = 1;
         b.add(j);
+    }
+    {   // weight gradients of both layers: 128 + 16 + 4 = 148 tiles at C1
+        b.phase();
+        b.add(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2));
+        b.add(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1));
+        b.add(b.colsum(e->dh1, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, B, 2 * H1, 1, 128));
     }
     e->ph_crit_adam = (int)e->phases.size();
     b.phase(); if (e->peer_mode) b.add(peer_signal(true)); b.add(adam(true));                // Adam(critic) [+ Polyak]
