@@ -435,3 +435,35 @@ def test_humanoid_shaped_update_matches_oracle(tf32x3):
     ga = actor_views(eng.layout, torch.from_numpy(eng.debug_read("grad_actor")), O, A, H)
     for k in ACTOR_KEYS:
         grads_close(ga[k].numpy(), o["actor_grads"][k], k)
+
+
+@pytest.mark.parametrize("n", [1, 7, 32])
+def test_acting_path_cluster_kernel_matches_oracle(n):
+    """`action, _ = actor(state)` per env step (sac/algorithm.py:233): n <= 32 rows run as ONE launch of an 8-CTA
+    thread-block cluster (activations exchanged through distributed shared memory).  Checked against the float64 oracle
+    and against the batched phase-program path (n > 32)."""
+    from torch_actor_critic_b200.networks.linear import Actor
+    O, A, H = 17, 6, [256, 256]
+    rng = np.random.default_rng(n)
+    actor_np, _ = onp.init_params(O, A, H, rng)
+    actor = Actor(O, A, H, act_limit=1.0)
+    actor.load_state_dict({k: torch.tensor(v) for k, v in actor_np.items()})
+    x = rng.standard_normal((n, O)).astype(np.float32)
+    eps = rng.standard_normal((n, A)).astype(np.float32)
+    hp = onp.HyperParams(act_limit=1.0)
+    a64 = onp.cast_params(actor_np, np.float64)
+    for det in (True, False):
+        pi, logp = actor(torch.tensor(x), deterministic=det, eps=None if det else torch.tensor(eps))
+        po, lo, _ = onp.actor_forward(a64, x.astype(np.float64), eps.astype(np.float64), hp, deterministic=det)
+        assert_close(pi.cpu().numpy(), po, 1e-5, 1e-6, "pi")
+        assert_close(logp.cpu().numpy(), lo, 1e-5, 2e-5, "logp")
+    # same rows through the batched path (40 rows -> phase programs), first n rows must agree
+    xb = np.concatenate([x, rng.standard_normal((40 - n, O)).astype(np.float32)]) if n < 40 else x
+    pb, lb = actor(torch.tensor(xb), deterministic=True)
+    ps, ls = actor(torch.tensor(x), deterministic=True)
+    assert torch.allclose(pb[:n], ps, rtol=1e-5, atol=1e-6) and torch.allclose(lb[:n], ls, rtol=1e-5, atol=2e-5)
+    # device-drawn noise: different draws on consecutive calls, actions inside the limit
+    p1, _ = actor(torch.tensor(x)); p2, _ = actor(torch.tensor(x))
+    assert not torch.equal(p1, p2) and float(p1.abs().max()) <= 1.0
+    pn, none = actor(torch.tensor(x), deterministic=True, with_logprob=False)
+    assert none is None and torch.equal(pn, ps)

@@ -16,6 +16,7 @@
 #include "../../include/sacb200.h"
 
 using namespace sacb;
+#include "sacb_act.cuh"
 
 // ------------------------------------------------------------------------------------------------------------
 // error plumbing
@@ -835,6 +836,27 @@ int sacb_actor_forward(sacb_handle e, const float* x, int32_t n, const float* ep
     CU(cudaSetDevice(e->cfg.device));
     if (int r = upload_programs(e, st)) return r;
     const int B = e->cfg.batch_size, O = e->cfg.obs_dim, A = e->cfg.act_dim;
+    {   // acting path (a handful of rows, e.g. one env step): one launch of an 8-CTA cluster, activations in DSMEM (sacb_act.cuh)
+        const size_t smem = act_smem_floats(n, O, A, e->cfg.hidden1, e->cfg.hidden2) * sizeof(float);
+        if (n >= 1 && n <= kActMaxRows && e->mode == 0 && smem <= 200 * 1024) {
+            const sacb_layout_info& L = e->lay;
+            ActArgs a;
+            memset(&a, 0, sizeof a);
+            a.x = x; a.w0 = e->pa + L.actor_w0; a.b0 = e->pa + L.actor_b0; a.w1 = e->pa + L.actor_w1; a.b1 = e->pa + L.actor_b1;
+            a.wh = e->pa + L.actor_w_mu; a.bh = e->pa + L.actor_b_mu;
+            a.eps = deterministic ? nullptr : eps_in; a.pi = pi; a.logp = logp;
+            a.n = n; a.O = O; a.A = A; a.H1 = e->cfg.hidden1; a.H2 = e->cfg.hidden2; a.deterministic = deterministic ? 1 : 0;
+            a.seed = e->cfg.seed + 0xA24BAED4963EE407ULL * (unsigned long long)(e->rank + 1);
+            a.counter = (e->rng_counter++) << 24;
+            a.log_min_std = e->cfg.log_min_std; a.log_max_std = e->cfg.log_max_std; a.act_limit = e->cfg.act_limit; a.flags = e->cfg.flags;
+            static bool attr_set = false;
+            if (!attr_set) { CU(cudaFuncSetAttribute(actor_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+            actor_act_kernel<<<kActCluster, 256, smem, st>>>(a);
+            CU(cudaGetLastError());
+            e->launches++;
+            return 0;
+        }
+    }
     for (int r0 = 0; r0 < n; r0 += B) {
         const int m = (n - r0) < B ? (n - r0) : B;
         CU(cudaMemcpy2DAsync(e->s2buf, e->lds * sizeof(float), x + (size_t)r0 * O, O * sizeof(float), O * sizeof(float), m,
