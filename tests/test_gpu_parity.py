@@ -437,11 +437,11 @@ def test_humanoid_shaped_update_matches_oracle(tf32x3):
         grads_close(ga[k].numpy(), o["actor_grads"][k], k)
 
 
-@pytest.mark.parametrize("n", [1, 7, 32])
+@pytest.mark.parametrize("n", [1, 3, 4])
 def test_acting_path_cluster_kernel_matches_oracle(n):
-    """`action, _ = actor(state)` per env step (sac/algorithm.py:233): n <= 32 rows run as ONE launch of an 8-CTA
+    """`action, _ = actor(state)` per env step (sac/algorithm.py:233): n <= 4 rows run as ONE launch of an 8-CTA
     thread-block cluster (activations exchanged through distributed shared memory).  Checked against the float64 oracle
-    and against the batched phase-program path (n > 32)."""
+    and against the batched phase-program path (n > 4)."""
     from torch_actor_critic_b200.networks.linear import Actor
     O, A, H = 17, 6, [256, 256]
     rng = np.random.default_rng(n)

@@ -14,7 +14,7 @@
 namespace cg = cooperative_groups;
 
 constexpr int kActCluster = 8;
-constexpr int kActMaxRows = 32;
+constexpr int kActMaxRows = 4;        // measured: 1 row 20.5 us host-bound (phase path 28.7); beyond ~4 rows the batched phase path wins
 
 struct ActArgs {
     const float* x;            // [n, O] caller's states
