@@ -459,7 +459,7 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     e->ldx = (int)r4(O + A); e->lds = (int)r4(O); e->ldh = (int)r4(2 * A); e->lddpi = (int)r4(A);
     e->tnH2 = (int)((H2 + e->tile_n - 1) / e->tile_n);
     const long long tn16_H2 = (H2 + 15) / 16, tn16_H1 = (H1 + 15) / 16;     // partial-tile counts of the finest tiling (tcgen05: N=16)
-    e->row_tiles = (int)((B + 7) / 8);
+    e->row_tiles = (int)((B + kRowsWarp - 1) / kRowsWarp);
     // carve the workspace
     size_t off = 0;
     auto take = [&](long long n) { size_t o = off; off += (size_t)r4(n); return o; };

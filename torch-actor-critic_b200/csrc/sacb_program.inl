@@ -61,7 +61,7 @@ static void build_programs(sacb_engine* e) {
         j.type = J_ROW_HEADS; j.A = e->heads; j.C = e->heads; j.lda = ldh; j.M = B; j.rows_dynamic = dyn;
         j.out0 = e->x2; j.out1 = e->logp; j.out2 = e->xp; j.out3 = e->logp + B; j.ldc = ldx; j.i0 = O;
         if (fuse_heads) { j.i1 = e->tnH2; j.B = e->hpart; j.i2 = B; j.bias = PA + L.actor_b_mu; }
-        j.ntiles = (B + 7) / 8; return j; };
+        j.ntiles = (B + kRowsHeads - 1) / kRowsHeads; return j; };
     // twin layer 0 as ONE [2*H1, O+A] GEMM, or (half = 0 / 1) only the q1 / q2 half of its output columns
     auto critic_l0 = [&](float* P, const float* X, float* H, int dyn, int b_static, int half = -1) {
         const int c0 = half < 0 ? 0 : half * H1, nc = half < 0 ? 2 * H1 : H1;
@@ -84,7 +84,7 @@ static void build_programs(sacb_engine* e) {
     auto gather = [&](int k_offset) {
         Job j = Builder::zero();
         j.type = J_GATHER; j.M = B; j.C = e->xs; j.out0 = e->xp; j.out1 = e->x2; j.ldc = ldx; j.out2 = e->s2buf; j.ldb = lds;
-        j.out3 = e->rd; j.ntiles = (B + 7) / 8; j.k_offset = k_offset;
+        j.out3 = e->rd; j.ntiles = (B + kRowsWarp - 1) / kRowsWarp; j.k_offset = k_offset;
         return j; };
     auto adam = [&](bool critic) {
         Job j = Builder::zero();
@@ -135,7 +135,7 @@ static void build_programs(sacb_engine* e) {
             Job j = Builder::zero();
             j.type = J_ROW_GHEAD; j.M = B; j.A = e->heads; j.lda = ldh; j.B = e->dpi; j.ldb = lddpi; j.C = e->ghead; j.ldc = ldh;
             if (fuse_dpi) { j.i1 = 2 * tnH1; j.B = e->dpart; j.i2 = B; }
-            j.ntiles = (B + 15) / 16;
+            j.ntiles = (B + kRowsGhead - 1) / kRowsGhead;
             b.add(j);
         }
         {
@@ -244,7 +244,7 @@ static void build_programs(sacb_engine* e) {
             b.phase();
             Job j = Builder::zero();
             j.type = J_ROW_QSUM; j.M = B; j.rows_dynamic = 1; j.A = e->qpart; j.i0 = B; j.i1 = e->tnH2;
-            j.bias = P + L.critic_b2[0]; j.out0 = e->qfw; j.ntiles = (B + 7) / 8;
+            j.bias = P + L.critic_b2[0]; j.out0 = e->qfw; j.ntiles = (B + kRowsWarp - 1) / kRowsWarp;
             b.add(j);
         }
         e->p_critic_fwd[w].end = (int)e->phases.size();

@@ -81,7 +81,7 @@ __device__ __forceinline__ void t5_load(char* buf, const float* __restrict__ g, 
             const float* src_row = g + (size_t)(o0 + row) * ld + k0;
             char* dst_row = buf + mg * kT5SboK + l8 * 16;
 #pragma unroll 4
-            for (int cb = warp / MG; cb < CB; cb += 8 / MG) {
+            for (int cb = warp / MG; cb < CB; cb += kWarps / MG) {
                 const int kk = (cb * 4 + c4) * 4;
                 if (kk < k_pad) {
                     int nb = 0;
@@ -102,7 +102,7 @@ __device__ __forceinline__ void t5_load(char* buf, const float* __restrict__ g, 
             char* dst_col = buf + (oo >> 5) * kT5LboMN + (oo & 7) * 4;
             const int og = (oo & 31) >> 3;
 #pragma unroll 4
-            for (int kg = warp / CB; kg < KG; kg += 8 / CB) {
+            for (int kg = warp / CB; kg < KG; kg += kWarps / CB) {
                 const int kk = kg * 8 + l8;
                 const int nb = kk < k_valid ? nb_o : 0;
                 cp_async16(dst_col + (kk >> 2) * SBO + (kk & 3) * 128 + 32 * (og ^ (kk & 3)), nb ? src_col + (size_t)kk * ld : g, nb);
