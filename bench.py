@@ -256,20 +256,21 @@ def run_gpu(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch") if args.workload == "c1" else None
     value = world * args.steps / (ms * 1e-3)
     e2e_v = world * args.steps / (ms_e2e * 1e-3)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 6), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "bf16" if args.precision == 3 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "update_every": UPDATE_EVERY, "batch_per_gpu": B,
-                   "gemm_arithmetic": "tensor-core 3xTF32 (fp32-level accuracy), fp32 accumulate" if args.precision else "fp32 FFMA", "global_batch": B * world,
+                   "gemm_arithmetic": GEMM_ARITH[args.precision], "global_batch": B * world,
                    "parallelism": f"dp{world}", "global_steps_per_s": round(args.steps / (ms * 1e-3), 1),
                    "samples_per_s": round(value * B, 1),
-                   "l2_policy": "inputs larger than L2: 165 MB replay ring, random-row gather; the 3.2 MB of weights/Adam "
-                                "state is the algorithm's working set and stays L2-resident by design",
-                   "value_definition": "batch-256 gradient updates summed over GPUs"},
+                   "l2_policy": f"inputs larger than L2: {N_BUF * ((2 * O + A + 1) * 4 + 1) / 1e6:.0f} MB replay ring, random-row gather; the "
+                                f"{(P_ACTOR + P_CRITIC) * 12 / 1e6 + P_CRITIC * 4 / 1e6:.1f} MB of weights/Adam state is the algorithm's "
+                                "working set and stays L2-resident by design",
+                   "value_definition": f"batch-{B} gradient updates summed over GPUs"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_v, 1), "unit": UNIT, "h2d_bytes_per_step": (2 * O + A + 1) * 4 + 1, "d2h_bytes_per_step": 8,
                 "path": "ReplayBuffer.store (host rows -> pinned staging -> HBM ring) + SAC.update_burst + loss readback per burst"},
@@ -278,7 +279,7 @@ def run_gpu(args):
                      "traffic": traffic, "peak_source": peak_src, "kernel": "sac_phase_kernel (persistent, 50 updates/launch)",
                      "kernel_ms_per_launch": round(k_ms, 4), "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * upd_per_launch,
                      "flops": {"achieved_tflops": round(FLOPS_PER_UPDATE * upd_per_launch / (k_ms * 1e-3) / 1e12, 3),
-                               "note": "fp32 FFMA path; latency-bound dependency chain of ~20 phases per update"}},
+                               "note": "latency-bound dependency chain of ~18 grid-synchronised phases per update"}},
     }
     if world == 1 and not args.no_cpu:
         rate, thr, done, probe, cores = cpu_baseline(arrays, 600, 20, budget_s=30.0)
@@ -286,6 +287,11 @@ def run_gpu(args):
                                 "sample": f"{done} updates at {thr} torch threads on the same synthetic arrays; thread probe "
                                           f"(updates/s) {probe}; host cpu_count={cores}"}
     print(json.dumps(line), flush=True)
+
+
+GEMM_ARITH = {0: "fp32 FFMA", 1: "tensor-core 3xTF32 via mma.sync (fp32-level accuracy), fp32 accumulate",
+              2: "tensor-core 3xTF32 via tcgen05/TMEM (fp32-level accuracy), fp32 accumulate",
+              3: "tcgen05 bf16 operands (rounded from fp32 on load), fp32 accumulate in TMEM, fp32 master weights/activations/Adam"}
 
 
 def set_workload(name):
@@ -308,7 +314,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", type=int, default=0, help="profiling only: 1 = one kernel launch per phase")
     ap.add_argument("--no-cpu", action="store_true", help="profiling only: skip the cpu_baseline leg")
-    ap.add_argument("--precision", type=int, default=1, help="1 = mma.sync 3xTF32 GEMMs (default), 0 = fp32 FFMA, 2 = tcgen05 3xTF32")
+    ap.add_argument("--precision", type=int, default=1, help="1 = mma.sync 3xTF32 GEMMs (default), 0 = fp32 FFMA, 2 = tcgen05 3xTF32, 3 = tcgen05 bf16 operands")
     ap.add_argument("--workload", default="c1", choices=["c1", "c2"],
                     help="c1 = BASELINE metric workload (default); c2 = Humanoid-shaped (obs=376, act=17, MLP 512x512, batch=1024), "
                          "fp32 storage -- side measurement only, not the bench line the driver reads")

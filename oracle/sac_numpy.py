@@ -73,6 +73,47 @@ def init_params(obs_dim: int, act_dim: int, hidden, rng: np.random.Generator, dt
     return actor, critic
 
 
+# --------------------------------------------------------------------------------------------
+# GEMM operand rounding (the "bf16 tensor-core MLP path" of BASELINE.json configs[2])
+# --------------------------------------------------------------------------------------------
+_OPERAND_ROUNDING = None          # None: products in the array dtype; "bf16": both operands rounded to bfloat16 first
+
+
+class operand_rounding:
+    """Context manager: inside it every dense-layer product (forward, dX, dW) of the hidden / head layers rounds BOTH
+    operands to bfloat16 (round-to-nearest-even) and accumulates in the array dtype -- the arithmetic of the CUDA
+    engine's precision-3 path.  The critics' scalar output layer ([1,H2]: a dot product, not a tensor-core GEMM) and
+    everything element-wise stay in the array dtype, as in the engine."""
+
+    def __init__(self, mode):
+        assert mode in (None, "bf16")
+        self.mode = mode
+
+    def __enter__(self):
+        global _OPERAND_ROUNDING
+        self.prev, _OPERAND_ROUNDING = _OPERAND_ROUNDING, self.mode
+
+    def __exit__(self, *exc):
+        global _OPERAND_ROUNDING
+        _OPERAND_ROUNDING = self.prev
+
+
+def round_bf16(x):
+    """float32 -> nearest bfloat16 (ties to even), returned as float32.  NaN/Inf pass through."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = x.view(np.uint32)
+    r = ((u.astype(np.uint64) + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    r = np.where(np.isfinite(x), r, u & np.uint32(0xFFFF0000) | np.where(np.isnan(x), np.uint32(0x00400000), np.uint32(0)))
+    return r.astype(np.uint32).view(np.float32).reshape(x.shape)
+
+
+def _mm(a, b):
+    if _OPERAND_ROUNDING == "bf16":
+        # products of two bfloat16 values are exact in float32; the accumulation runs in the array dtype
+        return round_bf16(a).astype(a.dtype) @ round_bf16(b).astype(a.dtype)
+    return a @ b
+
+
 def _softplus(x):
     """torch F.softplus(beta=1, threshold=20): x if x > 20 else log1p(exp(x))."""
     with np.errstate(over="ignore"):
@@ -91,10 +132,10 @@ def actor_forward(p, x, eps, hp: HyperParams, deterministic=False):
 
     Returns (pi_action [B,A], logp [B], cache)."""
     dt = x.dtype
-    h1 = np.maximum(x @ p["layers.0.weight"].T + p["layers.0.bias"], 0)            # :33-35
-    h2 = np.maximum(h1 @ p["layers.1.weight"].T + p["layers.1.bias"], 0)
-    mu = h2 @ p["mu_layer.weight"].T + p["mu_layer.bias"]                          # :37
-    ls_raw = h2 @ p["log_std_layer.weight"].T + p["log_std_layer.bias"]            # :38
+    h1 = np.maximum(_mm(x, p["layers.0.weight"].T) + p["layers.0.bias"], 0)        # :33-35
+    h2 = np.maximum(_mm(h1, p["layers.1.weight"].T) + p["layers.1.bias"], 0)
+    mu = _mm(h2, p["mu_layer.weight"].T) + p["mu_layer.bias"]                      # :37
+    ls_raw = _mm(h2, p["log_std_layer.weight"].T) + p["log_std_layer.bias"]        # :38
     ls = np.clip(ls_raw, dt.type(hp.log_min_std), dt.type(hp.log_max_std))         # :39
     std = np.exp(ls)                                                               # :40
     u = mu if deterministic else (mu + eps * std).astype(dt)                       # :43-45
@@ -117,8 +158,8 @@ def actor_forward(p, x, eps, hp: HyperParams, deterministic=False):
 def critic_forward(p, q, s, a):
     """Critic.forward, networks/linear.py:61-69, for sub-critic `q` in {"q1","q2"}."""
     x = np.concatenate([s, a], axis=-1)                                             # :62
-    h1 = np.maximum(x @ p[f"{q}.layers.0.weight"].T + p[f"{q}.layers.0.bias"], 0)   # :63-65
-    h2 = np.maximum(h1 @ p[f"{q}.layers.1.weight"].T + p[f"{q}.layers.1.bias"], 0)
+    h1 = np.maximum(_mm(x, p[f"{q}.layers.0.weight"].T) + p[f"{q}.layers.0.bias"], 0)   # :63-65
+    h2 = np.maximum(_mm(h1, p[f"{q}.layers.1.weight"].T) + p[f"{q}.layers.1.bias"], 0)
     out = (h2 @ p[f"{q}.layers.2.weight"].T + p[f"{q}.layers.2.bias"])[..., 0]      # :67-68
     return out, dict(x=x, h1=h1, h2=h2)
 
@@ -139,15 +180,15 @@ def _critic_backward(p, q, cache, dq, need_param_grads=True):
     W0 = p[f"{q}.layers.0.weight"]
     W2 = p[f"{q}.layers.2.weight"]
     dh2 = (dq[:, None] * W2) * (cache["h2"] > 0)              # relu'(pre) = (out > 0)
-    dh1 = (dh2 @ W1) * (cache["h1"] > 0)
-    dx = dh1 @ W0
+    dh1 = _mm(dh2, W1) * (cache["h1"] > 0)
+    dx = _mm(dh1, W0)
     g = {}
     if need_param_grads:
         g[f"{q}.layers.2.weight"] = (dq[None, :] @ cache["h2"])
         g[f"{q}.layers.2.bias"] = dq.sum(keepdims=True)
-        g[f"{q}.layers.1.weight"] = dh2.T @ cache["h1"]
+        g[f"{q}.layers.1.weight"] = _mm(dh2.T, cache["h1"])
         g[f"{q}.layers.1.bias"] = dh2.sum(0)
-        g[f"{q}.layers.0.weight"] = dh1.T @ cache["x"]
+        g[f"{q}.layers.0.weight"] = _mm(dh1.T, cache["x"])
         g[f"{q}.layers.0.bias"] = dh1.sum(0)
     return g, dx
 
@@ -210,15 +251,15 @@ def pi_loss_and_grads(actor, critic, batch, eps, hp: HyperParams):
     g_ls = (g_u * eps_ * std - glogp) * inside
     h2, h1, x = c["h2"], c["h1"], c["x"]
     g = {}
-    g["mu_layer.weight"] = g_mu.T @ h2
+    g["mu_layer.weight"] = _mm(g_mu.T, h2)
     g["mu_layer.bias"] = g_mu.sum(0)
-    g["log_std_layer.weight"] = g_ls.T @ h2
+    g["log_std_layer.weight"] = _mm(g_ls.T, h2)
     g["log_std_layer.bias"] = g_ls.sum(0)
-    dh2 = (g_mu @ actor["mu_layer.weight"] + g_ls @ actor["log_std_layer.weight"]) * (h2 > 0)
-    g["layers.1.weight"] = dh2.T @ h1
+    dh2 = (_mm(g_mu, actor["mu_layer.weight"]) + _mm(g_ls, actor["log_std_layer.weight"])) * (h2 > 0)
+    g["layers.1.weight"] = _mm(dh2.T, h1)
     g["layers.1.bias"] = dh2.sum(0)
-    dh1 = (dh2 @ actor["layers.1.weight"]) * (h1 > 0)
-    g["layers.0.weight"] = dh1.T @ x
+    dh1 = _mm(dh2, actor["layers.1.weight"]) * (h1 > 0)
+    g["layers.0.weight"] = _mm(dh1.T, x)
     g["layers.0.bias"] = dh1.sum(0)
     grads = {k: g[k].astype(dt) for k in ACTOR_KEYS}
     aux = dict(pi=pi, logp_pi=logp, q1_pi=q1, q2_pi=q2)

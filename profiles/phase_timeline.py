@@ -19,10 +19,18 @@ PHASES = ["gather(first only)", "A.L0+C.L0q1", "A.L1(+heads)+C.L1q1+C.L0q2", "ro
           "A.dWh+dh2", "A.dW1+dh1", "A.dW0+losspi", "adam_a+gather(k+1)"]
 
 
+# unfused program (2A > 16 or the bf16 path): heads and d-pi are GEMM phases of their own
+PHASES_UNFUSED = ["gather(first only)", "A.L0+C.L0q1", "A.L1+C.L1q1+C.L0q2", "A.heads+C.L1q2", "rows_heads", "T.L0", "T.L1",
+                  "row_backup", "C.dh1+db1+dW2+lossq", "C.dW1+dW0+db0", "adam_c+polyak", "Cpi.L0", "Cpi.L1", "row_pi", "Cpi.dh1",
+                  "dpi", "row_ghead", "A.dWh+dh2", "A.dW1+dh1", "A.dW0+losspi", "adam_a+gather(k+1)"]
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     from torch_actor_critic_b200.engine import Engine, actor_views, critic_views
     O, A, H, B, N = 17, 6, [256, 256], 256, 1_000_000
+    if os.environ.get("SACB_WORKLOAD", "c1") == "c2":           # Humanoid shapes (BASELINE configs[2])
+        O, A, H, B, N = 376, 17, [512, 512], 1024, 200_000
     eng = Engine(O, A, H, batch_size=B, max_burst=50, device=0, act_limit=1.0)
     dev = eng.tdev()
     pa, pc = eng.new_actor_arena(), eng.new_critic_arena()
@@ -42,7 +50,7 @@ def main():
     torch.cuda.synchronize()
     st = eng.profile_phases(n).astype(np.int64)              # [n, P, ctas, 2]
     nP, nC = st.shape[1], st.shape[2]
-    names = PHASES if nP == len(PHASES) else [f"p{i}" for i in range(nP)]
+    names = PHASES if nP == len(PHASES) else PHASES_UNFUSED if nP == len(PHASES_UNFUSED) else [f"p{i}" for i in range(nP)]
     work_end = st[..., 0].max(axis=2)                        # slowest CTA done with its tiles
     bar_end = st[..., 1].max(axis=2)                         # everyone past the barrier
     first_work_end = np.where(st[..., 0] > 0, st[..., 0], np.iinfo(np.int64).max).min(axis=2)

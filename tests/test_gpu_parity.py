@@ -438,6 +438,77 @@ def test_humanoid_shaped_update_matches_oracle(tf32x3):
         grads_close(ga[k].numpy(), o["actor_grads"][k], k)
 
 
+@pytest.mark.parametrize("shape", ["humanoid", "ragged"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bf16_tensor_core_path_matches_bf16_oracle(shape, mode):
+    """BASELINE config 3 ("Humanoid-shaped ..., bf16 tensor-core MLP path"): precision 3 = tcgen05 GEMMs with bf16
+    operands (rounded to nearest-even on the way into shared memory), fp32 accumulation in TMEM, fp32 master weights,
+    activations and Adam.  Checked against the float64 oracle with the SAME operand rounding (oracle.operand_rounding),
+    so the comparison only has to absorb accumulation order plus the rare element whose bf16 rounding flips because its
+    fp32 value differs in the last bits (relative 2^-9 on that element).  Stated tolerance: losses rtol 1e-3; per-sample
+    quantities rtol 2e-3 / atol 2e-3.  Gradients: every layer re-rounds its input to bf16, so a last-bit difference
+    upstream flips roundings downstream and two correct implementations agree only down to the bf16 noise floor of a
+    K-term sum (~2^-9 / sqrt(K) of the tensor's scale): |err| <= 1e-2 |g| + 2e-2 rms(g) for at least 99% of a tensor's
+    entries and max |err| <= 0.1 max |g|.  "ragged": tile tails in every dimension (M < 128, N < 64, K not a multiple of 16, unaligned
+    rows -> element-wise staging)."""
+    from torch_actor_critic_b200.engine import Engine, actor_views, critic_views
+    if shape == "humanoid":
+        O, A, H, B, N, lim = 376, 17, [512, 512], 1024, 4096, 0.4
+    else:
+        O, A, H, B, N, lim = 11, 3, [72, 40], 96, 700, 1.0
+    rng = np.random.default_rng(5)
+    actor, critic = onp.init_params(O, A, H, rng)
+    arrays = dict(state=rng.standard_normal((N, O)).astype(np.float32), actions=rng.uniform(-lim, lim, (N, A)).astype(np.float32),
+                  rewards=rng.standard_normal(N).astype(np.float32), next_state=rng.standard_normal((N, O)).astype(np.float32),
+                  done=rng.random(N) < 0.05)
+    idx = rng.choice(N, B, replace=False)[None]
+    eps = rng.standard_normal((1, 2, B, A)).astype(np.float32)
+    eng = Engine(O, A, H, batch_size=B, max_burst=2, device=0, act_limit=lim)
+    eng.set_precision(3)
+    eng.set_mode(mode)
+    pa, pc = eng.new_actor_arena(), eng.new_critic_arena()
+    for k, v in actor_views(eng.layout, pa, O, A, H).items():
+        v.copy_(torch.from_numpy(actor[k]))
+    for k, v in critic_views(eng.layout, pc, O, A, H).items():
+        v.copy_(torch.from_numpy(critic[k]))
+    pt = pc.clone()
+    eng.bind_params(pa, pc, pt)
+    eng.bind_adam(eng.new_actor_arena(), eng.new_actor_arena(), 0, eng.new_critic_arena(), eng.new_critic_arena(), 0)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in arrays.items()}
+    eng.bind_buffer(t["state"], t["actions"], t["rewards"], t["next_state"], t["done"])
+    eng.set_buffer_state(0, N)
+    lq, lp = eng.update(1, idx=idx, eps=eps)
+    hp = onp.HyperParams(act_limit=lim)
+    a64, c64, t64 = (onp.cast_params(p, np.float64) for p in (actor, critic, critic))
+    with onp.operand_rounding("bf16"):
+        o = onp.sac_update(a64, c64, t64, onp.AdamState.zeros_like(a64), onp.AdamState.zeros_like(c64),
+                           batch_from(arrays, idx[0], np.float64), eps[0, 0].astype(np.float64), eps[0, 1].astype(np.float64), hp)
+        # the same update WITHOUT operand rounding must be measurably different, or this test proves nothing
+    o32 = onp.sac_update(*(onp.cast_params(p, np.float64) for p in (actor, critic, critic)), onp.AdamState.zeros_like(a64),
+                         onp.AdamState.zeros_like(c64), batch_from(arrays, idx[0], np.float64), eps[0, 0].astype(np.float64),
+                         eps[0, 1].astype(np.float64), hp)
+    assert np.abs(o32["q1"] - o["q1"]).max() > 1e-4
+    assert_close(lq.cpu().numpy(), [o["loss_q"]], 1e-3, 1e-4, "loss_q")
+    assert_close(lp.cpu().numpy(), [o["loss_pi"]], 1e-3, 1e-4, "loss_pi")
+    assert abs(float(lq) - o["loss_q"]) < 0.5 * abs(o32["loss_q"] - o["loss_q"]) + 1e-5      # closer to the bf16 oracle than to fp32
+    for key in ("backup", "q1", "q2", "logp_next", "logp_pi", "a2", "pi", "q1_pi", "q2_pi"):
+        assert_close(eng.debug_read(key), o[key], 2e-3, 2e-3, key)
+
+    def grads_close(got, want, name):
+        got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+        err = np.abs(got - want)
+        rms = float(np.sqrt(np.mean(want * want)))
+        bad = err > 2e-2 * rms + 1e-2 * np.abs(want)
+        assert bad.mean() <= 1e-2 and err.max() <= 0.1 * np.abs(want).max() + 1e-7, \
+            f"{name}: {bad.sum()} of {bad.size} entries off, max err {err.max():.3e}, rms {rms:.3e}"
+    gc = critic_views(eng.layout, torch.from_numpy(eng.debug_read("grad_critic")), O, A, H)
+    for k in CRITIC_KEYS:
+        grads_close(gc[k].numpy(), o["critic_grads"][k], k)
+    ga = actor_views(eng.layout, torch.from_numpy(eng.debug_read("grad_actor")), O, A, H)
+    for k in ACTOR_KEYS:
+        grads_close(ga[k].numpy(), o["actor_grads"][k], k)
+
+
 @pytest.mark.parametrize("n", [1, 3, 4])
 def test_acting_path_cluster_kernel_matches_oracle(n):
     """`action, _ = actor(state)` per env step (sac/algorithm.py:233): n <= 4 rows run as ONE launch of an 8-CTA

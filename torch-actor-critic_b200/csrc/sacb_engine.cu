@@ -95,7 +95,7 @@ struct sacb_engine {
     int num_sms = 0, grid_coop = 0, grid_std = 0, grid_t5 = 0;
     int tile_m = kBM, tile_n = kBN;       // GEMM tile of the active arithmetic path (64x16 for tcgen05)
     int mode = 0;
-    int tf32x3 = 1;                 // GEMM precision: 1 = tensor cores with 3xTF32 compensation, 0 = fp32 FFMA
+    int tf32x3 = 1;                 // GEMM arithmetic: 0 fp32 FFMA, 1 3xTF32 mma.sync (default), 2 3xTF32 tcgen05, 3 bf16 tcgen05
     long long launches = 0;
     // bound arenas
     float *pa = nullptr, *pc = nullptr, *pt = nullptr;
@@ -372,6 +372,7 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
     ra.grad_div = (float)e->world;
     ra.flags = c.flags;
     ra.O = c.obs_dim; ra.A = c.act_dim; ra.H1 = c.hidden1; ra.H2 = c.hidden2; ra.B = c.batch_size;
+    ra.s2_stride = (long long)c.batch_size * e->lds;
     ra.pass_mask = 3;
 }
 
@@ -389,7 +390,7 @@ static int run_phases(sacb_engine* e, RunArgs ra, int pb, int pe, int kb, int ke
                 ra.phase_begin = p; ra.phase_end = p + 1; ra.k_begin = k; ra.k_end = k + 1; ra.use_barrier = 0;
                 int nt = e->phases[p].ntiles;
                 int grid = nt < 1 ? 1 : nt;
-                if (e->tf32x3 == 2) sac_phase_kernel<true><<<grid, kThreads, kSmemBytesT5, st>>>(ra);
+                if (e->tf32x3 >= 2) sac_phase_kernel<true><<<grid, kThreads, kSmemBytesT5, st>>>(ra);
                 else sac_phase_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(ra);
                 CU(cudaGetLastError());
                 e->launches++;
@@ -399,7 +400,7 @@ static int run_phases(sacb_engine* e, RunArgs ra, int pb, int pe, int kb, int ke
     ra.phase_begin = pb; ra.phase_end = pe; ra.k_begin = kb; ra.k_end = ke; ra.use_barrier = 1;
     CU(cudaMemsetAsync(e->barrier, 0, sizeof(unsigned long long), st));
     void* args[] = {&ra};
-    if (e->tf32x3 == 2)
+    if (e->tf32x3 >= 2)
         CU(cudaLaunchCooperativeKernel((void*)sac_phase_kernel<true>, dim3(e->grid_coop), dim3(kThreads), args, kSmemBytesT5, st));
     else
         CU(cudaLaunchCooperativeKernel((void*)sac_phase_kernel<false>, dim3(e->grid_coop), dim3(kThreads), args, kSmemBytes, st));
@@ -466,7 +467,7 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     struct Slot { float** p; size_t o; };
     std::vector<Slot> slots;
     auto want = [&](float*& p, long long n) { slots.push_back({&p, take(n)}); };
-    want(e->xs, B * e->ldx); want(e->xp, B * e->ldx); want(e->x2, B * e->ldx); want(e->s2buf, B * e->lds); want(e->rd, 2 * B);
+    want(e->xs, B * e->ldx); want(e->xp, B * e->ldx); want(e->x2, B * e->ldx); want(e->s2buf, 2 * B * e->lds); want(e->rd, 2 * B);
     want(e->ah1, B * H1); want(e->ah2, B * H2); want(e->heads, B * e->ldh); want(e->logp, 2 * B);
     want(e->ch1, B * 2 * H1); want(e->ch2, B * 2 * H2); want(e->th1, B * 2 * H1); want(e->th2, B * 2 * H2);
     want(e->qpart, 2LL * tn16_H2 * B); want(e->qtpart, 2LL * tn16_H2 * B); want(e->qbuf, 9 * B); want(e->qfw, 2 * B);
@@ -1062,13 +1063,14 @@ int64_t sacb_launch_count(sacb_handle e) { return e ? e->launches : 0; }
 
 int sacb_set_precision(sacb_handle e, int32_t tf32x3) {
     if (!e) return fail(SACB_ERR_INVALID, "null handle");
-    if (tf32x3 < 0 || tf32x3 > 2) return fail(SACB_ERR_INVALID, "precision must be 0 (fp32 FFMA), 1 (3xTF32 mma.sync) or 2 (3xTF32 tcgen05)");
-    if (tf32x3 == 2 && e->grid_t5 < 1) return fail(SACB_ERR_CUDA, "tcgen05 path does not fit on this device");
+    if (tf32x3 < 0 || tf32x3 > 3)
+        return fail(SACB_ERR_INVALID, "precision must be 0 (fp32 FFMA), 1 (3xTF32 mma.sync), 2 (3xTF32 tcgen05) or 3 (bf16 tcgen05)");
+    if (tf32x3 >= 2 && e->grid_t5 < 1) return fail(SACB_ERR_CUDA, "tcgen05 path does not fit on this device");
     e->tf32x3 = tf32x3;
-    e->tile_m = tf32x3 == 2 ? 64 : kBM;
-    e->tile_n = tf32x3 == 2 ? 16 : kBN;
+    e->tile_m = tf32x3 == 3 ? kBfM : tf32x3 == 2 ? kT5M : kBM;
+    e->tile_n = tf32x3 == 3 ? kBfN : tf32x3 == 2 ? kT5N : kBN;
     e->tnH2 = (e->cfg.hidden2 + e->tile_n - 1) / e->tile_n;
-    e->grid_coop = tf32x3 == 2 ? e->grid_t5 : e->grid_std;
+    e->grid_coop = tf32x3 >= 2 ? e->grid_t5 : e->grid_std;
     e->dirty = true;                                   // tile shapes are baked into the phase programs
     return 0;
 }

@@ -38,14 +38,27 @@ static void build_programs(sacb_engine* e) {
     float *PA = e->pa, *PC = e->pc, *PT = e->pt, *GA = e->ga, *GC = e->gc;
     const long long sW1 = L.critic_w1[1] - L.critic_w1[0];
     const int row_tiles = e->row_tiles;
-    const bool fuse_heads = 2 * A <= 16, fuse_dpi = A <= 16;
+    // bf16 path: every matrix product is a GEMM job of its own (bf16 operands), nothing rides in an fp32 epilogue
+    const bool fuse_heads = 2 * A <= 16 && e->tf32x3 != 3, fuse_dpi = A <= 16 && e->tf32x3 != 3;
     const int tnH1 = (H1 + e->tile_n - 1) / e->tile_n;
     const bool actor_sync = !(c.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC);
+    // One GPU, mma.sync / FFMA tiles: nothing sits between backward() and optimizer.step(), so every job that finishes a
+    // gradient (dW tiles, bias column sums, the loss reduction's db2) applies Adam (+ Polyak) in its own epilogue and the two
+    // Adam phases disappear (18 -> 16 phases).  In-place parameter updates must not race with a dX GEMM that reads the
+    // same weights in the same phase, so the actor's dW jobs run one phase after the dX through that layer.
+    const bool fuse_adam = e->world <= 1 && !e->peer_mode && e->tf32x3 < 2;
+    auto with_adam = [&](Job j, bool critic) {
+        if (!fuse_adam) return j;
+        const long long off = j.C - (critic ? GC : GA);
+        j.adam = critic ? 2 : 1;
+        j.out0 = (critic ? e->mc : e->ma) + off; j.out1 = (critic ? e->vc : e->va) + off;
+        j.out2 = (critic ? PC : PA) + off; j.out3 = critic ? PT + off : nullptr;
+        return j; };
 
     // ---- job factories -------------------------------------------------------------------------------------------
     auto actor_l0 = [&](int dyn, int b_static) {
         Job j = b.gemm(G_FWD, E_BIAS_RELU, e->s2buf, lds, 0, PA + L.actor_w0, O, 0, e->ah1, H1, 0, B, H1, O, 1, dyn);
-        j.bias = PA + L.actor_b0; j.b_static = b_static; return j; };
+        j.bias = PA + L.actor_b0; j.b_static = b_static; if (fuse_adam && !dyn) j.stg = 1; return j; };
     auto actor_l1 = [&](int dyn) {
         Job j = b.gemm(G_FWD, E_BIAS_RELU, e->ah1, H1, 0, PA + L.actor_w1, H1, 0, e->ah2, H2, 0, B, H2, H1, 1, dyn);
         j.bias = PA + L.actor_b1; j.b_static = 1;
@@ -85,6 +98,7 @@ static void build_programs(sacb_engine* e) {
         Job j = Builder::zero();
         j.type = J_GATHER; j.M = B; j.C = e->xs; j.out0 = e->xp; j.out1 = e->x2; j.ldc = ldx; j.out2 = e->s2buf; j.ldb = lds;
         j.out3 = e->rd; j.ntiles = (B + kRowsWarp - 1) / kRowsWarp; j.k_offset = k_offset;
+        if (fuse_adam) j.stg = 4;
         return j; };
     auto adam = [&](bool critic) {
         Job j = Builder::zero();
@@ -138,30 +152,41 @@ static void build_programs(sacb_engine* e) {
             j.ntiles = (B + kRowsGhead - 1) / kRowsGhead;
             b.add(j);
         }
-        {
-            b.phase();
-            b.add(b.gemm(G_DW, E_STORE, e->ghead, ldh, 0, e->ah2, H2, 0, GA + L.actor_w_mu, H2, 0, 2 * A, H2, B, 1));
-            b.add(b.colsum(e->ghead, ldh, 0, nullptr, 0, GA + L.actor_b_mu, 0, B, 2 * A, 1));
+        // A.dh2 | A.dh1 | (nothing): the dX chain;  A.dWh | A.dW1 | A.dW0: weight gradients.  Unfused, layer L's dW rides
+        // with the dX through layer L (3 phases + Adam).  Fused Adam updates the weights in place, so dW_L moves one phase
+        // later than the dX that reads W_L: [dh2] [dWh, dh1] [dW1, dW0] -- still 3 phases, no Adam phase.
+        auto dWh = [&]() {
+            b.add(with_adam(b.gemm(G_DW, E_STORE, e->ghead, ldh, 0, e->ah2, H2, 0, GA + L.actor_w_mu, H2, 0, 2 * A, H2, B, 1), false));
+            b.add(with_adam(b.colsum(e->ghead, ldh, 0, nullptr, 0, GA + L.actor_b_mu, 0, B, 2 * A, 1), false)); };
+        auto dh2 = [&]() {
             Job j = b.gemm(G_DX, E_MASK, e->ghead, ldh, 0, PA + L.actor_w_mu, H2, 0, e->adh2, H2, 0, B, H2, 2 * A, 1);
             j.mask = e->ah2; j.ldmask = H2; j.b_static = 1;
-            b.add(j);
-        }
-        {
-            b.phase();
-            b.add(b.gemm(G_DW, E_STORE, e->adh2, H2, 0, e->ah1, H1, 0, GA + L.actor_w1, H1, 0, H2, H1, B, 1));
-            b.add(b.colsum(e->adh2, H2, 0, nullptr, 0, GA + L.actor_b1, 0, B, H2, 1));
+            b.add(j); };
+        auto dW1 = [&]() {
+            b.add(with_adam(b.gemm(G_DW, E_STORE, e->adh2, H2, 0, e->ah1, H1, 0, GA + L.actor_w1, H1, 0, H2, H1, B, 1), false));
+            b.add(with_adam(b.colsum(e->adh2, H2, 0, nullptr, 0, GA + L.actor_b1, 0, B, H2, 1), false)); };
+        auto dh1 = [&]() {
             Job j = b.gemm(G_DX, E_MASK, e->adh2, H2, 0, PA + L.actor_w1, H1, 0, e->adh1, H1, 0, B, H1, H2, 1);
             j.mask = e->ah1; j.ldmask = H1; j.b_static = 1;
+            b.add(j); };
+        auto dW0 = [&]() {
+            Job j = with_adam(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->s2buf, lds, 0, GA + L.actor_w0, O, 0, H1, O, B, 1), false);
+            if (fuse_adam) j.stg = 2;          // the next batch's s' is being gathered into the other buffer during this phase
             b.add(j);
-        }
-        {
-            b.phase();
-            b.add(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->s2buf, lds, 0, GA + L.actor_w0, O, 0, H1, O, B, 1));
-            b.add(b.colsum(e->adh1, H1, 0, nullptr, 0, GA + L.actor_b0, 0, B, H1, 1));
+            b.add(with_adam(b.colsum(e->adh1, H1, 0, nullptr, 0, GA + L.actor_b0, 0, B, H1, 1), false)); };
+        auto loss_pi = [&]() {
             Job j = Builder::zero();
             j.type = J_REDUCE_PI; j.A = e->lparts_pi; j.i0 = row_tiles; j.out0 = e->loss_scalar + 1; j.ntiles = 1;
-            b.add(j);
+            b.add(j); };
+        if (fuse_adam) {
+            b.phase(); dh2(); loss_pi();
+            b.phase(); dWh(); dh1();
+            int last = b.phase(); dW1(); dW0();
+            return last;
         }
+        b.phase(); dWh(); dh2();
+        b.phase(); dW1(); dh1();
+        b.phase(); dW0(); loss_pi();
         int adam_phase = b.phase();
         if (e->peer_mode && actor_sync) b.add(peer_signal(false));
         { Job j = adam(false); if (!actor_sync) j.i2 = 0; b.add(j); }
@@ -194,21 +219,29 @@ static void build_programs(sacb_engine* e) {
         // loss reduction) fit on the SMs the GEMM tiles leave idle: 128 + 8 + 8 + 1 = 145 tiles at C1
         b.phase();
         b.add(critic_dx1(false));
-        b.add(b.colsum(e->dh2, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, B, 2 * H2, 1, 64));
-        b.add(b.colsum(e->ch2, 2 * H2, H2, e->qbuf + 5 * (size_t)B, B, GC + L.critic_w2[0], H2, B, H2, 2, 64));
+        b.add(with_adam(b.colsum(e->dh2, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, B, 2 * H2, 1, 64), true));
+        b.add(with_adam(b.colsum(e->ch2, 2 * H2, H2, e->qbuf + 5 * (size_t)B, B, GC + L.critic_w2[0], H2, B, H2, 2, 64), true));
         Job j = Builder::zero();
         j.type = J_REDUCE_Q; j.A = e->lparts_q; j.i0 = row_tiles; j.out0 = e->loss_scalar; j.out1 = GC + L.critic_b2[0];
         j.out2 = GC + L.critic_b2[1]; j.ntiles = 1;
+        if (fuse_adam) {
+            j.adam = 2; j.aux0 = PC + L.critic_b2[0]; j.aux1 = e->mc + L.critic_b2[0]; j.aux2 = e->vc + L.critic_b2[0];
+            j.aux3 = PT + L.critic_b2[0]; j.sAux = (long long)(L.critic_b2[1] - L.critic_b2[0]);
+        }
         b.add(j);
     }
     {   // weight gradients of both layers: 128 + 16 + 4 = 148 tiles at C1
         b.phase();
-        b.add(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2));
-        b.add(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1));
-        b.add(b.colsum(e->dh1, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, B, 2 * H1, 1, 128));
+        b.add(with_adam(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2), true));
+        b.add(with_adam(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1), true));
+        b.add(with_adam(b.colsum(e->dh1, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, B, 2 * H1, 1, 128), true));
     }
-    e->ph_crit_adam = (int)e->phases.size();
-    b.phase(); if (e->peer_mode) b.add(peer_signal(true)); b.add(adam(true));                // Adam(critic) [+ Polyak]
+    if (fuse_adam) {
+        e->ph_crit_adam = (int)e->phases.size() - 1;        // "the phase that ends update_critic": the fused dW + Adam phase
+    } else {
+        e->ph_crit_adam = (int)e->phases.size();
+        b.phase(); if (e->peer_mode) b.add(peer_signal(true)); b.add(adam(true));            // Adam(critic) [+ Polyak]
+    }
     e->ph_pi_begin = (int)e->phases.size();
     e->ph_pi_adam = policy_tail(false);
     b.add(gather(1));                                      // prefetch the next update's batch (staging tiles are idle here)

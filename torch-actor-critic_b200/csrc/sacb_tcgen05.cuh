@@ -151,7 +151,10 @@ __device__ __forceinline__ void t5_split(char* hi, char* lo, int k_valid) {
     }
 }
 
-struct T5Ctx { unsigned tmem; unsigned mbar; unsigned phase; };   // TMEM base address, mbarrier smem address, its parity
+struct T5Ctx {
+    unsigned tmem; unsigned mbar; unsigned phase;     // TMEM base address, mbarrier smem address, its parity
+    unsigned mbar_op0, mbar_op1, phase_op;            // bf16 path: one mbarrier per operand buffer; parity bit b of phase_op
+};
 
 template <bool A_RC, bool B_RC>
 __device__ __forceinline__ void gemm_tile_t5(const Job& jb, int tile, char* pipe, const RunArgs& ra, T5Ctx& cx) {
@@ -297,4 +300,285 @@ __device__ __forceinline__ void gemm_tile_t5(const Job& jb, int tile, char* pipe
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                           // TMEM and smem are reused by the next tile
     TR(104);
+}
+
+// ==========================================================================================================
+// bf16 tensor-core path (precision 3): C[128 x 64] = sum_r bf16(A(i,r)) * bf16(B(j,r)), fp32 accumulate in TMEM.
+// The BASELINE "Humanoid-shaped, bf16 tensor-core MLP path" config: fp32 master weights / activations / Adam stay as
+// they are in L2; every GEMM operand is rounded to bf16 (round-to-nearest-even) on its way into shared memory.
+//
+//   K is consumed in chunks of 64.  Per chunk: cp.async the fp32 operand tiles into a staging buffer (two in flight),
+//   all threads convert staging -> bf16 UMMA operand tiles (always K-major SWIZZLE_NONE, whatever the global layout:
+//   the conversion transposes output-contiguous operands), one thread issues 4 tcgen05.mma (M=128, N=64, K=16) and
+//   commits to the mbarrier that guards that operand buffer.  Two operand buffers, so the tensor core works on chunk c
+//   while chunk c+1 is being converted and chunk c+2 is landing.
+//       bf16 K-major canonical layout: byte(o, k) = (o/8)*1024 + (k/8)*128 + (o%8)*16 + (k%8)*2     (LBO 128, SBO 1024)
+//   Accumulator: 128 TMEM lanes = 128 rows, 64 fp32 columns; thread t < 128 finishes row t (tcgen05.ld.32x32b).
+// ==========================================================================================================
+constexpr int kBfM = 128, kBfN = 64, kBfK = 64;
+constexpr int kBfPitchRC = kBfK + 4;                                    // staging pitch (floats), reduction-contiguous
+constexpr int kBfStageAFloats = kBfM * kBfPitchRC;                      // 8704 (>= 64 * (128 + 4) for the other layout)
+constexpr int kBfStageBFloats = kBfN * kBfPitchRC;                      // 4352 (= 64 * (64 + 4))
+constexpr int kBfStageBytes = (kBfStageAFloats + kBfStageBFloats) * 4;  // 52,224
+constexpr int kBfOpABytes = kBfM * kBfK * 2, kBfOpBBytes = kBfN * kBfK * 2;
+constexpr int kBfOpOff = 2 * kBfStageBytes;                             // 104,448
+constexpr int kBfEpiOff = kBfOpOff + 2 * (kBfOpABytes + kBfOpBBytes);   // 153,600: bias[64], w2[64]
+constexpr int kBfMaskOff = kBfEpiOff + 2 * kBfN * 4;                    // 154,112: relu-mask tile [128][68] fp32
+static_assert(kBfMaskOff + kBfM * kBfPitchRC * 4 <= kT5PipeBytes, "bf16 tile buffers must fit in the tcgen05 kernel's shared memory");
+static_assert(kBfK * (kBfM + 4) <= kBfStageAFloats && kBfK * (kBfN + 4) <= kBfStageBFloats, "staging holds either layout");
+
+__device__ __forceinline__ unsigned bf_idesc() {
+    // c_format F32 (1) [4,6) | a_format BF16 (1) [7,10) | b_format BF16 (1) [10,13) | both K-major | N>>3 [17,23) | M>>4 [24,29)
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kBfN >> 3) << 17) | ((unsigned)(kBfM >> 4) << 24);
+}
+__device__ __forceinline__ void bf_mma(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ unsigned bf_pack(float lo, float hi) {
+    unsigned r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // first source -> upper half
+    return r;
+}
+
+// fp32 operand tile (R outputs x 64 reduction elements from (o0, k0)) -> staging.  RC: [R][68]; OC: [64][R+4].
+// The issue cost of these copies is what bounds a chunk (measured: 12 cp.async per thread cost ~1,300 cycles with
+// per-copy index math), so every thread derives ONE base pointer and walks it with a compile-time stride.
+template <bool RC, int R>
+__device__ __forceinline__ void bf_stage(float* s, const float* __restrict__ g, int ld, int o0, int o_valid, int k0, int k_valid, int vec) {
+    constexpr int P = RC ? kBfPitchRC : R + 4;
+    const int t = threadIdx.x;
+    if (vec) {
+        if (RC) {                        // thread -> (row t/16 + 16q, 4 k's at (t%16)*4)
+            const int o = t >> 4, r = (t & 15) << 2;
+            const int nbk = r < k_valid ? min(4, k_valid - r) * 4 : 0;
+            const float* src = g + (size_t)(o0 + o) * ld + k0 + r;
+            float* dst = s + o * P + r;
+            const size_t step = (size_t)16 * ld;
+#pragma unroll
+            for (int q = 0; q < (R * 16) / kThreads; ++q) {
+                const int nb = (o + 16 * q < o_valid) ? nbk : 0;
+                cp_async16(dst + q * 16 * P, nb ? src : g, nb);
+                src += step;
+            }
+        } else {                         // thread -> (k-row t/VR + (256/VR)q, 4 outputs at (t%VR)*4)
+            constexpr int VR = R / 4, RS = kThreads / VR;
+            const int r = t / VR, o = (t % VR) << 2;
+            const int nbo = o < o_valid ? min(4, o_valid - o) * 4 : 0;
+            const float* src = g + (size_t)(k0 + r) * ld + o0 + o;
+            float* dst = s + r * P + o;
+            const size_t step = (size_t)RS * ld;
+#pragma unroll
+            for (int q = 0; q < kBfK / RS; ++q) {
+                const int nb = (r + RS * q < k_valid) ? nbo : 0;
+                cp_async16(dst + q * RS * P, nb ? src : g, nb);
+                src += step;
+            }
+        }
+    } else {            // element-wise path for unaligned operands; the reduction tail is zero-filled to a multiple of 16
+        const int k_pad = min(kBfK, (k_valid + 15) & ~15);
+#pragma unroll 4
+        for (int e = t; e < R * kBfK; e += kThreads) {
+            const int o = RC ? e >> 6 : e % R, r = RC ? e & 63 : e / R;       // R and 64 are powers of two: shifts
+            if (o < o_valid && r < k_pad) {
+                float* dst = RC ? s + o * P + r : s + r * P + o;
+                if (r < k_valid) cp_async4(dst, RC ? g + (size_t)(o0 + o) * ld + k0 + r : g + (size_t)(k0 + r) * ld + o0 + o);
+                else *dst = 0.f;
+            }
+        }
+    }
+}
+
+// staging (fp32) -> bf16 K-major UMMA tile.  One thread = one 16-byte chunk (8 consecutive k of one output row);
+// consecutive threads take consecutive rows, so a quarter-warp writes one contiguous 128-byte core matrix.
+template <bool RC, int R>
+__device__ __forceinline__ void bf_convert(const float* st, char* op, int k_valid) {
+    constexpr int P = RC ? kBfPitchRC : R + 4;
+    const int nkc = (min(kBfK, (k_valid + 15) & ~15)) >> 3;
+    for (int c = threadIdx.x; c < R * nkc; c += kThreads) {
+        const int o = c % R, kc = c / R;
+        float x[8];
+        if (RC) {
+            const float4 a = *reinterpret_cast<const float4*>(st + o * P + kc * 8);
+            const float4 b = *reinterpret_cast<const float4*>(st + o * P + kc * 8 + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = st[(kc * 8 + q) * P + o];
+        }
+        uint4 pk;
+        pk.x = bf_pack(x[0], x[1]); pk.y = bf_pack(x[2], x[3]); pk.z = bf_pack(x[4], x[5]); pk.w = bf_pack(x[6], x[7]);
+        *reinterpret_cast<uint4*>(op + (o >> 3) * 1024 + kc * 128 + (o & 7) * 16) = pk;
+    }
+}
+
+__device__ __forceinline__ void bf_wait(T5Ctx& cx, int b) {
+    mbar_wait(b ? cx.mbar_op1 : cx.mbar_op0, (cx.phase_op >> b) & 1u);
+    cx.phase_op ^= 1u << b;
+}
+
+template <bool A_RC, bool B_RC>
+__device__ __forceinline__ void gemm_tile_bf16(const Job& jb, int tile, char* pipe, const RunArgs& ra, T5Ctx& cx) {
+    const int M = (jb.rows_dynamic && ra.m_rows > 0) ? min(jb.M, ra.m_rows) : jb.M;
+    const int N = jb.N, K = jb.K;
+    const int tn = jb.tn;
+    const int z = (tile >= jb.tpz) ? 1 : 0;
+    const int rem = tile - z * jb.tpz;
+    const int ti = rem / tn, tj = rem - ti * tn;
+    const int i0 = ti * kBfM, j0 = tj * kBfN;
+    if (i0 >= M) return;                                   // uniform per CTA
+    const int i_valid = min(kBfM, M - i0), j_valid = min(kBfN, N - j0);
+    const float* __restrict__ Ag = jb.A + (size_t)z * jb.sA;
+    const float* __restrict__ Bg = jb.B + (size_t)z * jb.sB;
+    const int warp = threadIdx.x >> 5;
+    float* s_bias = reinterpret_cast<float*>(pipe + kBfEpiOff);
+    float* s_w2 = s_bias + kBfN;
+    const bool has_bias = jb.epi == E_BIAS || jb.epi == E_BIAS_RELU || jb.epi == E_BIAS_RELU_DOT;
+
+    const int nch = (K + kBfK - 1) / kBfK;
+    auto issue = [&](int c) {
+        float* sa = reinterpret_cast<float*>(pipe + (c & 1) * kBfStageBytes);
+        float* sb = sa + kBfStageAFloats;
+        const int k0 = c * kBfK, kv = min(kBfK, K - k0);
+        bf_stage<A_RC, kBfM>(sa, Ag, jb.lda, i0, i_valid, k0, kv, jb.a_vec);
+        bf_stage<B_RC, kBfN>(sb, Bg, jb.ldb, j0, j_valid, k0, kv, jb.b_vec);
+    };
+    issue(0);
+    // relu mask of the tile (E_MASK) rides in the first cp.async group: its L2 latency hides behind the K loop
+    float* s_mask = reinterpret_cast<float*>(pipe + kBfMaskOff);
+    const bool mask_vec = jb.epi == E_MASK && j_valid == kBfN && (jb.ldmask & 3) == 0 && (jb.sMask & 3) == 0;   // tile-uniform
+    if (mask_vec) {
+        const float* mp = jb.mask + (size_t)z * jb.sMask + (size_t)i0 * jb.ldmask + j0;
+#pragma unroll
+        for (int q = 0; q < (kBfM * 16) / kThreads; ++q) {
+            const int v = threadIdx.x + q * kThreads, o = v >> 4, r = (v & 15) << 2;
+            cp_async16(s_mask + o * kBfPitchRC + r, o < i_valid ? mp + (size_t)o * jb.ldmask + r : mp, o < i_valid ? 16 : 0);
+        }
+    }
+    cp_async_commit();
+    if (nch > 1) issue(1);
+    cp_async_commit();
+    // epilogue operands -> shared memory
+    if (threadIdx.x < kBfN) s_bias[threadIdx.x] = (has_bias && j0 + threadIdx.x < N) ? __ldcg(jb.bias + (size_t)z * jb.sBias + j0 + threadIdx.x) : 0.f;
+    else if (threadIdx.x < 2 * kBfN) {
+        const int c = threadIdx.x - kBfN;
+        s_w2[c] = (jb.epi == E_BIAS_RELU_DOT && j0 + c < N) ? __ldcg(jb.aux0 + (size_t)z * jb.sAux + j0 + c) : 0.f;
+    }
+
+    const unsigned idesc = bf_idesc();
+    for (int c = 0; c < nch; ++c) {
+        const int b = c & 1;
+        const int kv = min(kBfK, K - c * kBfK);
+        TR(200);
+        cp_async_wait<1>();                                 // chunk c has landed (one younger group may be in flight)
+        __syncthreads();
+        TR(201);
+        if (c >= 2) bf_wait(cx, b);
+        TR(202);                         // MMAs of chunk c-2 are done with this operand buffer
+        const float* sa = reinterpret_cast<const float*>(pipe + b * kBfStageBytes);
+        char* oa = pipe + kBfOpOff + b * (kBfOpABytes + kBfOpBBytes);
+        char* ob = oa + kBfOpABytes;
+        bf_convert<A_RC, kBfM>(sa, oa, kv);
+        bf_convert<B_RC, kBfN>(sa + kBfStageAFloats, ob, kv);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the tensor core
+        __syncthreads();
+        TR(203);
+        if (c + 2 < nch) issue(c + 2);                      // the staging buffer just converted is free again
+        cp_async_commit();
+        TR(204);
+        if (threadIdx.x == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            unsigned long long da = t5_desc(smem_u32(oa), 128u, 1024u, false), db = t5_desc(smem_u32(ob), 128u, 1024u, false);
+            const int nk16 = (kv + 15) >> 4;
+            for (int k16 = 0; k16 < nk16; ++k16) {
+                bf_mma(cx.tmem, da, db, idesc, (c == 0 && k16 == 0) ? 0u : 1u);
+                da += 16; db += 16;                         // two 128-byte chunk columns per K=16 step (16-byte units)
+            }
+            t5_commit(b ? cx.mbar_op1 : cx.mbar_op0);
+        }
+    }
+    TR(205);
+    cp_async_wait<0>();
+    // consume the outstanding commits in order (the last one covers every MMA of the tile)
+    if (nch >= 2) bf_wait(cx, (nch - 2) & 1);
+    bf_wait(cx, (nch - 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    TR(206);
+
+    // ---- epilogue, two steps so that all 256 threads work and every global access is coalesced (a thread-per-row
+    // epilogue on 4 warps cost ~7,000 cycles per tile):
+    //   1. TMEM -> shared memory, raw accumulators.  A warp may only read the TMEM lane quarter (warp % 4), so warps w and
+    //      w+4 share rows 32(w%4)..+31 and take 32 columns each (two tcgen05.ld.32x32b.x16, one wait).
+    //   2. 16 threads per row (float4 each): + bias, relu / relu-mask, Q-dot partial (shuffle over the 16 lanes), store.
+    float* s_out = reinterpret_cast<float*>(pipe);             // [128][68] in the idle staging buffer
+    {
+        const int lane = threadIdx.x & 31, q4 = warp & 3, half = warp >> 2;
+        unsigned r0[16], r1[16];
+        const unsigned taddr = cx.tmem + ((unsigned)(32 * q4) << 16) + (unsigned)(half * 32);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                     : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]),
+                       "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                     : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+                       "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+                     : "r"(taddr + 16u));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* dst = s_out + (32 * q4 + lane) * kBfPitchRC + half * 32;
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+            *reinterpret_cast<uint4*>(dst + c) = make_uint4(r0[c], r0[c + 1], r0[c + 2], r0[c + 3]);
+            *reinterpret_cast<uint4*>(dst + 16 + c) = make_uint4(r1[c], r1[c + 1], r1[c + 2], r1[c + 3]);
+        }
+    }
+    __syncthreads();
+    {
+        const bool relu = jb.epi == E_BIAS_RELU || jb.epi == E_BIAS_RELU_DOT;
+        float* __restrict__ cbase = jb.C + (size_t)z * jb.sC + (size_t)i0 * jb.ldc + j0;
+        const bool store_vec = j_valid == kBfN && (jb.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0);
+        const int c4 = (threadIdx.x & 15) << 2;
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c4), w4 = *reinterpret_cast<const float4*>(s_w2 + c4);
+#pragma unroll
+        for (int q = 0; q < (kBfM * 16) / kThreads; ++q) {       // 16 threads per row: 256 contiguous bytes
+            const int row = (threadIdx.x >> 4) + 16 * q;
+            const bool rok = row < i_valid;
+            float4 x = *reinterpret_cast<const float4*>(s_out + row * kBfPitchRC + c4);
+            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if (jb.epi == E_MASK) {
+                float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mask_vec) m = *reinterpret_cast<const float4*>(s_mask + row * kBfPitchRC + c4);
+                else if (rok) {
+                    const float* mp = jb.mask + (size_t)z * jb.sMask + (size_t)(i0 + row) * jb.ldmask + j0 + c4;
+                    if (c4 + 0 < j_valid) m.x = __ldcg(mp); if (c4 + 1 < j_valid) m.y = __ldcg(mp + 1);
+                    if (c4 + 2 < j_valid) m.z = __ldcg(mp + 2); if (c4 + 3 < j_valid) m.w = __ldcg(mp + 3);
+                }
+                x.x = m.x > 0.f ? x.x : 0.f; x.y = m.y > 0.f ? x.y : 0.f; x.z = m.z > 0.f ? x.z : 0.f; x.w = m.w > 0.f ? x.w : 0.f;
+            }
+            if (c4 + 0 >= j_valid) x.x = 0.f;
+            if (c4 + 1 >= j_valid) x.y = 0.f;
+            if (c4 + 2 >= j_valid) x.z = 0.f;
+            if (c4 + 3 >= j_valid) x.w = 0.f;
+            if (jb.epi == E_BIAS_RELU_DOT) {                     // Q-dot partial of this row over the tile's 64 columns
+                float dot = fmaf(x.x, w4.x, fmaf(x.y, w4.y, fmaf(x.z, w4.z, x.w * w4.w)));
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                if (rok && (threadIdx.x & 15) == 0) jb.out0[((size_t)z * tn + tj) * jb.i0 + i0 + row] = dot;
+            }
+            if (rok) {
+                float* dst = cbase + (size_t)row * jb.ldc + c4;
+                if (store_vec) *reinterpret_cast<float4*>(dst) = x;
+                else {
+                    if (c4 + 0 < j_valid) dst[0] = x.x;
+                    if (c4 + 1 < j_valid) dst[1] = x.y;
+                    if (c4 + 2 < j_valid) dst[2] = x.z;
+                    if (c4 + 3 < j_valid) dst[3] = x.w;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                           // TMEM and smem are reused by the next tile
+    TR(207);
 }
