@@ -81,6 +81,13 @@ def main():
         print(f"{names[i]:<24}{work[i]:>14.2f}{fastest[i]:>14.2f}{barrier[i]:>10.2f}{work[i] + barrier[i]:>9.2f}")
     print(f"{'SUM':<24}{work.sum():>14.2f}{'':>14}{barrier.sum():>10.2f}{(work + barrier).sum():>9.2f}")
     print(f"per update (stamps): {per_update:.2f} us  -> {1e6 / per_update:.0f} updates/s")
+    # SACB_DUMP_PHASES="8,16": per-CTA time from the previous phase's end to "tiles done" for those phases (update 2),
+    # CTA i runs tile i of a one-round phase, so this attributes the phase's critical path to a job
+    for p in [int(x) for x in os.environ.get("SACB_DUMP_PHASES", "").split(",") if x]:
+        k = min(2, n - 1)
+        prev = max(st[k, p - 1, :, 1].max(), st[k, p - 1, :, 0].max())
+        d = (st[k, p, :, 0] - prev) / 1e3
+        print(f"# phase {p} per-CTA work (us): " + " ".join(f"{x:.1f}" for x in d))
 
 
 if __name__ == "__main__":

@@ -1027,7 +1027,8 @@ int sacb_debug_profile(sacb_handle e, int32_t n_updates, uint64_t* out, int64_t 
     if (int r = draw_indices(e, e->idx_buf, n_updates, B, st)) return r;
     if (int r = draw_normals(e, e->eps_buf, (long long)n_updates * 2 * B * A, st)) return r;
 #ifdef SACB_TRACE
-    { int z = 0; cudaMemcpyToSymbol(g_trace_n, &z, sizeof(int)); }
+    { int z = 0; cudaMemcpyToSymbol(g_trace_n, &z, sizeof(int));
+      const char* tc = getenv("SACB_TRACE_CTA"); int cta = tc ? atoi(tc) : 0; cudaMemcpyToSymbol(g_trace_cta, &cta, sizeof(int)); }
 #endif
     RunArgs ra;
     fill_args(e, ra);

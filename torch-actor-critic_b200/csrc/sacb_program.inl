@@ -81,11 +81,13 @@ static void build_programs(sacb_engine* e) {
         Job j = b.gemm(G_FWD, E_BIAS_RELU, X, ldx, 0, P + L.critic_w0[0] + (size_t)c0 * OA, OA, 0, H + c0, 2 * H1, 0, B, nc, OA, 1, dyn);
         j.bias = P + L.critic_b0[0] + c0; j.b_static = b_static; return j; };
     // z0 .. z0+nz-1 of the twin layer 1 (with the Q-dot epilogue)
-    auto critic_l1 = [&](float* P, const float* Hin, float* Hout, float* part, int dyn, int z0, int nz) {
-        Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, Hin + (size_t)z0 * H1, 2 * H1, H1, P + L.critic_w1[z0], H1, sW1,
-                       Hout + (size_t)z0 * H2, 2 * H2, H2, B, H2, H1, nz, dyn);
+    // (row0, nrows): only that block of batch rows -- lets a GEMM be spread over the idle CTAs of two phases
+    auto critic_l1 = [&](float* P, const float* Hin, float* Hout, float* part, int dyn, int z0, int nz, int row0 = 0, int nrows = -1) {
+        if (nrows < 0) nrows = B;
+        Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, Hin + (size_t)z0 * H1 + (size_t)row0 * 2 * H1, 2 * H1, H1, P + L.critic_w1[z0], H1, sW1,
+                       Hout + (size_t)z0 * H2 + (size_t)row0 * 2 * H2, 2 * H2, H2, nrows, H2, H1, nz, dyn);
         j.bias = P + L.critic_b1[z0]; j.sBias = H2; j.aux0 = P + L.critic_w2[z0]; j.sAux = H2;
-        j.out0 = part + (size_t)z0 * e->tnH2 * B; j.i0 = B; j.b_static = 1;
+        j.out0 = part + (size_t)z0 * e->tnH2 * B + row0; j.i0 = B; j.b_static = 1;
         return j; };
     auto critic_dx1 = [&](bool with_dpi) {       // dh1 = (dh2 . W1) * relu'(h1)   [+ d pi partials]
         Job j = b.gemm(G_DX, E_MASK, e->dh2, 2 * H2, H2, PC + L.critic_w1[0], H1, sW1, e->dh1, 2 * H1, H1, B, H1, H2, 2);
@@ -114,7 +116,32 @@ static void build_programs(sacb_engine* e) {
         return j; };
 
     // actor trunk + heads + tanh-Gaussian rows; `with_critic` interleaves the online critic's forward (update_critic)
+    // Tile budget of update_critic's forward part (one round = one tile per SM, `cap` tiles): the online critic's forward
+    // (C.L0 / C.L1, two halves each) has slack until the backup rows, so its tiles fill the CTAs the actor / target GEMMs
+    // leave idle.  When C.L0[q2] would not fit next to A.L1 and C.L1[q1] (C1: 64 + 64 + 64 > 148), C.L1[q1] and most of
+    // C.L1[q2] move next to the tanh-Gaussian rows and the last row blocks of C.L1[q2] next to T.L1.
+    const int cap = e->grid_coop > 0 ? e->grid_coop : 148;
+    const int t_l1 = ((B + e->tile_m - 1) / e->tile_m) * e->tnH2;                 // tiles of one [B, H2] layer-1 GEMM
+    const int t_l0 = ((B + e->tile_m - 1) / e->tile_m) * tnH1;                    // ... of one [B, H1] layer-0 GEMM
+    const int t_rows = (B + kRowsHeads - 1) / kRowsHeads;
+    int q2_late_rows = 0;                                                          // rows of C.L1[q2] deferred to the T.L1 phase
+    bool spread = false;
+    if (fuse_heads && t_l1 + t_l1 + t_l0 > cap && t_l1 + t_l0 <= cap) {
+        spread = true;
+        const int room = cap - t_rows - t_l1;                                      // tiles left next to rows_heads + C.L1[q1]
+        const int blocks_fit = room > 0 ? room / e->tnH2 : 0, blocks = (B + e->tile_m - 1) / e->tile_m;
+        const int late_blocks = blocks_fit >= blocks ? 0 : blocks - blocks_fit;
+        q2_late_rows = late_blocks * e->tile_m;
+        if (2 * t_l1 + late_blocks * e->tnH2 > cap || q2_late_rows >= B) { spread = false; q2_late_rows = 0; }
+    }
     auto actor_forward = [&](int dyn, bool with_critic, int l0_static) {
+        if (with_critic && spread) {
+            b.phase(); b.add(actor_l0(dyn, l0_static)); b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 0));
+            b.phase(); b.add(actor_l1(dyn)); b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 1));
+            b.phase(); b.add(row_heads(dyn)); b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 1));
+            b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1, 0, B - q2_late_rows));
+            return;
+        }
         // tile budget: one round = one tile per SM.  A.L0 + C.L0[q1] (e.g. 64 + 64 tiles) now, C.L0[q2] rides as the
         // cheap second tile of the next phase (its consumer C.L1[q2] runs one phase later anyway)
         b.phase(); b.add(actor_l0(dyn, l0_static)); if (with_critic) b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 0));
@@ -206,6 +233,7 @@ static void build_programs(sacb_engine* e) {
     actor_forward(0, true, /*actor W0 was just written by Adam(actor) of the previous update*/ 0);
     b.phase(); b.add(critic_l0(PT, e->x2, e->th1, 0, 1));                                   // target critic on (s', a2)
     b.phase(); b.add(critic_l1(PT, e->th1, e->th2, e->qtpart, 0, 0, 2));
+    if (spread && q2_late_rows > 0) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1, B - q2_late_rows, q2_late_rows));
     {   // backup + dq + dh2 (sac/algorithm.py:63-72)
         b.phase();
         Job j = Builder::zero();
