@@ -183,14 +183,14 @@ static void build_programs(sacb_engine* e) {
         // with the dX through layer L (3 phases + Adam).  Fused Adam updates the weights in place, so dW_L moves one phase
         // later than the dX that reads W_L: [dh2] [dWh, dh1] [dW1, dW0] -- still 3 phases, no Adam phase.
         auto dWh = [&]() {
-            b.add(with_adam(b.gemm(G_DW, E_STORE, e->ghead, ldh, 0, e->ah2, H2, 0, GA + L.actor_w_mu, H2, 0, 2 * A, H2, B, 1), false));
+            { Job j = with_adam(b.gemm(G_DW, E_STORE, e->ghead, ldh, 0, e->ah2, H2, 0, GA + L.actor_w_mu, H2, 0, 2 * A, H2, B, 1), false); j.b_static = 1; b.add(j); }
             b.add(with_adam(b.colsum(e->ghead, ldh, 0, nullptr, 0, GA + L.actor_b_mu, 0, B, 2 * A, 1), false)); };
         auto dh2 = [&]() {
             Job j = b.gemm(G_DX, E_MASK, e->ghead, ldh, 0, PA + L.actor_w_mu, H2, 0, e->adh2, H2, 0, B, H2, 2 * A, 1);
             j.mask = e->ah2; j.ldmask = H2; j.b_static = 1;
             b.add(j); };
         auto dW1 = [&]() {
-            b.add(with_adam(b.gemm(G_DW, E_STORE, e->adh2, H2, 0, e->ah1, H1, 0, GA + L.actor_w1, H1, 0, H2, H1, B, 1), false));
+            { Job j = with_adam(b.gemm(G_DW, E_STORE, e->adh2, H2, 0, e->ah1, H1, 0, GA + L.actor_w1, H1, 0, H2, H1, B, 1), false); j.b_static = 1; b.add(j); }
             b.add(with_adam(b.colsum(e->adh2, H2, 0, nullptr, 0, GA + L.actor_b1, 0, B, H2, 1), false)); };
         auto dh1 = [&]() {
             Job j = b.gemm(G_DX, E_MASK, e->adh2, H2, 0, PA + L.actor_w1, H1, 0, e->adh1, H1, 0, B, H1, H2, 1);
@@ -199,6 +199,7 @@ static void build_programs(sacb_engine* e) {
         auto dW0 = [&]() {
             Job j = with_adam(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->s2buf, lds, 0, GA + L.actor_w0, O, 0, H1, O, B, 1), false);
             if (fuse_adam) j.stg = 2;          // the next batch's s' is being gathered into the other buffer during this phase
+            j.b_static = 1;
             b.add(j);
             b.add(with_adam(b.colsum(e->adh1, H1, 0, nullptr, 0, GA + L.actor_b0, 0, B, H1, 1), false)); };
         auto loss_pi = [&]() {
@@ -260,8 +261,10 @@ static void build_programs(sacb_engine* e) {
     }
     {   // weight gradients of both layers: 128 + 16 + 4 = 148 tiles at C1
         b.phase();
-        b.add(with_adam(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2), true));
-        b.add(with_adam(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1), true));
+        // B operands of weight-gradient GEMMs are forward activations nobody writes during the backward pass: prefetchable
+        auto st = [](Job j) { j.b_static = 1; return j; };
+        b.add(st(with_adam(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2), true)));
+        b.add(st(with_adam(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1), true)));
         b.add(with_adam(b.colsum(e->dh1, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, B, 2 * H1, 1, 128), true));
     }
     if (fuse_adam) {
