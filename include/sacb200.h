@@ -175,8 +175,12 @@ int sacb_debug_profile(sacb_handle h, int32_t n_updates, uint64_t* stamps_host, 
                        int32_t* n_ctas, uintptr_t stream);
 /* Number of kernel launches the engine has enqueued so far (bench `gpu_launches`). */
 int64_t sacb_launch_count(sacb_handle h);
-/* GEMM arithmetic: 1 (default) = tensor cores with 3xTF32 error compensation (fp32-level accuracy: every product is
- * a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation), 0 = plain fp32 FFMA. */
+/* GEMM arithmetic.  1 (default) = mma.sync tensor cores with 3xTF32 error compensation (fp32-level accuracy: every
+ * product is a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation); 0 = plain fp32 FFMA; 2 = the same 3xTF32
+ * arithmetic on tcgen05 with TMEM accumulators; 3 = tcgen05 with bf16 operands (rounded to nearest-even from the fp32
+ * tensors on load), fp32 accumulation in TMEM, fp32 master weights / activations / Adam -- the "bf16 tensor-core MLP
+ * path" of the Humanoid-shaped configuration.  Nothing the reference exposes corresponds to this call: its arithmetic is
+ * whatever torch CPU does (networks/linear.py:33-38). */
 int sacb_set_precision(sacb_handle h, int32_t tf32x3);
 /* Execution mode: 0 = persistent cooperative kernel (default), 1 = one launch per phase (debug / profiling). */
 int sacb_set_mode(sacb_handle h, int32_t mode);

@@ -1,18 +1,19 @@
 // sacb_program.inl -- the phase programs (included by sacb_engine.cu after Builder / sacb_engine are defined).
 //
-// Program of ONE SAC gradient update (reference sac/algorithm.py:275-278), 18 grid-synchronised phases:
+// Program of ONE SAC gradient update (reference sac/algorithm.py:275-278).  With a gradient exchange between backward
+// and optimizer step (world > 1) it has 18 grid-synchronised phases:
 //
 //   P0*  gather(k)                                   (* first update of a launch only; later batches are prefetched)
 //   ---- update_critic (sac/algorithm.py:115-141) ----
-//   P1   A.L0 (s' -> ah1)                  ||  C.L0 twin ([s|a] -> ch1)
-//   P2   A.L1 (+ heads as post-product)    ||  C.L1[q1] (+ Q-dot)
-//   P3   tanh-Gaussian rows (a2, logp | pi, logp)  ||  C.L1[q2] (+ Q-dot)
+//   P1   A.L0 (s' -> ah1)                  ||  C.L0[q1] ([s|a] -> ch1)
+//   P2   A.L1 (+ heads as post-product)    ||  C.L0[q2]
+//   P3   tanh-Gaussian rows (a2, logp | pi, logp)  ||  C.L1[q1] (+ Q-dot)  ||  C.L1[q2], first row blocks
 //   P4   T.L0 twin ([s'|a2] -> th1)
-//   P5   T.L1 twin (+ Q-dot)
+//   P5   T.L1 twin (+ Q-dot)               ||  C.L1[q2], remaining row blocks
 //   P6   backup / dq / dh2 rows
-//   P7   C.dh1 twin  ||  db1  ||  dW2
-//   P8   C.dW1 twin  ||  C.dW0  ||  db0  ||  loss_q, db2
-//   P9   [NCCL]  Adam(critic) + Polyak
+//   P7   C.dh1 twin  ||  db1  ||  dW2  ||  loss_q, db2
+//   P8   C.dW1 twin  ||  C.dW0  ||  db0
+//   P9   [exchange]  Adam(critic) + Polyak
 //   ---- update_policy (sac/algorithm.py:143-162) ----
 //   P10  Cpi.L0 twin ([s|pi] -> ch1)
 //   P11  Cpi.L1 twin (+ Q-dot)
@@ -22,10 +23,16 @@
 //   P15  A.dWh || dbh || A.dh2
 //   P16  A.dW1 || db1 || A.dh1
 //   P17  A.dW0 || db0 || loss_pi
-//   P18  [NCCL]  Adam(actor)  ||  gather(k+1)
+//   P18  [exchange]  Adam(actor)  ||  gather(k+1)
 //
-// The two post-products need 2A <= 16 resp. A <= 16; wider action spaces fall back to a separate heads GEMM / d-pi
-// GEMM phase (generic path, exercised by the Humanoid-shaped test).
+// On ONE GPU (mma.sync / FFMA tiles) the Adam step and the Polyak move are applied by the jobs that finish a gradient, in
+// their epilogues (Job.adam), P9 and P18 disappear (16 phases) and the actor's backward becomes
+//   P15' A.dh2 || loss_pi      P16' A.dWh+Adam || dbh+Adam || A.dh1      P17' A.dW1+Adam || db1 || A.dW0+Adam || db0 || gather(k+1)
+// (a weight matrix is stepped one phase after the dX GEMM that reads it; the s' staging tile is parity double-buffered
+// because the gather of the next batch now overlaps A.dW0, which still reads this batch's s').
+//
+// The two post-products need 2A <= 16 resp. A <= 16; wider action spaces, and the bf16 path, use a separate heads GEMM /
+// d-pi GEMM phase (generic path, exercised by the Humanoid-shaped tests).
 
 static void build_programs(sacb_engine* e) {
     e->jobs.clear();

@@ -351,5 +351,6 @@ class Engine:
         check(self._lib.sacb_set_mode(self._h, int(mode)))
 
     def set_precision(self, tf32x3):
-        """1 (default): tensor-core GEMMs with 3xTF32 error compensation; 0: plain fp32 FFMA."""
+        """1 (default): mma.sync tensor-core GEMMs with 3xTF32 error compensation; 0: plain fp32 FFMA; 2: 3xTF32 on
+        tcgen05/TMEM; 3: tcgen05 with bf16 operands, fp32 accumulation (Humanoid-shaped "bf16 MLP" configuration)."""
         check(self._lib.sacb_set_precision(self._h, int(tf32x3)))
