@@ -139,3 +139,84 @@ def test_replay_buffer_oracle_matches_reference():
     assert str(g["empty_sample_error"]) == "ValueError"
     with pytest.raises(ValueError):
         onp.ReplayBufferOracle(4, 3, 2).gather([0])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bf16 operand-rounding mode of the oracle (the checker of the engine's precision-3 path)
+# ---------------------------------------------------------------------------------------------------------------
+def test_round_bf16_is_torch_bfloat16():
+    import torch
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(200_000).astype(np.float32) * np.float32(10.0) ** rng.integers(-30, 30, 200_000).astype(np.float32),
+                        np.array([0.0, -0.0, np.inf, -np.inf, 1 + 2 ** -8, 1 + 3 * 2 ** -8, 1 + 2 ** -9, 3.3895314e38, 1e-40, -1e-45], np.float32)])
+    want = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    got = onp.round_bf16(x)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))            # bit for bit, ties to even, overflow to inf
+    assert np.isnan(onp.round_bf16(np.array([np.nan], np.float32))[0])
+    with onp.operand_rounding("bf16"):                                          # products of rounded operands, fp accumulation
+        a, b = rng.standard_normal((5, 7)).astype(np.float32), rng.standard_normal((7, 3)).astype(np.float32)
+        assert np.array_equal(onp._mm(a, b), onp.round_bf16(a) @ onp.round_bf16(b))
+    assert np.array_equal(onp._mm(a, b), a @ b)                                 # and the mode is off again outside
+
+
+def test_bf16_oracle_matches_torch_autograd_with_rounded_operands(monkeypatch):
+    """Independent restatement of the bf16 arithmetic: torch autograd with a custom Linear whose forward rounds both
+    operands to bfloat16 and whose backward rounds the incoming gradient and uses the rounded saved operands -- i.e. every
+    product of the hidden / head layers has bf16 operands, everything else (relu, tanh-Gaussian, losses, the scalar output
+    layer of the critics) is plain autograd.  The hand-derived numpy backward in operand_rounding("bf16") mode must agree."""
+    import torch
+    import torch.nn.functional as F
+    import oracle.sac_torch_cpu as otc
+
+    class Bf16Linear(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w, b):
+            xr, wr = x.bfloat16().to(x.dtype), w.bfloat16().to(w.dtype)
+            ctx.save_for_backward(xr, wr)
+            return xr @ wr.T + b
+
+        @staticmethod
+        def backward(ctx, g):
+            xr, wr = ctx.saved_tensors
+            gr = g.bfloat16().to(g.dtype)
+            return gr @ wr, gr.T @ xr, g.sum(0)
+
+    class FShim:
+        relu, softplus = staticmethod(F.relu), staticmethod(F.softplus)
+
+        @staticmethod
+        def linear(x, w, b):
+            return F.linear(x, w, b) if w.shape[0] == 1 else Bf16Linear.apply(x, w, b)
+
+    monkeypatch.setattr(otc, "F", FShim)
+    torch.set_num_threads(1)
+    O, A, H, B, N = 11, 3, [72, 40], 96, 400
+    rng = np.random.default_rng(7)
+    actor, critic = onp.init_params(O, A, H, rng)
+    arrays = dict(state=rng.standard_normal((N, O)).astype(np.float32), actions=rng.uniform(-1, 1, (N, A)).astype(np.float32),
+                  rewards=rng.standard_normal(N).astype(np.float32), next_state=rng.standard_normal((N, O)).astype(np.float32),
+                  done=rng.random(N) < 0.05)
+    idx = rng.choice(N, B, replace=False)
+    eps = rng.standard_normal((2, B, A)).astype(np.float32)
+    hp = onp.HyperParams(act_limit=1.0)
+    sac = otc.TorchCpuSAC(actor, critic, hp)
+    ot = sac.update({k: torch.tensor(v) for k, v in batch_from(arrays, idx).items()}, torch.tensor(eps[0]), torch.tensor(eps[1]))
+    a32, c32, t32 = ({k: v.copy() for k, v in p.items()} for p in (actor, critic, critic))
+    with onp.operand_rounding("bf16"):
+        on = onp.sac_update(a32, c32, t32, onp.AdamState.zeros_like(a32), onp.AdamState.zeros_like(c32),
+                            batch_from(arrays, idx), eps[0], eps[1], hp)
+    on32 = onp.sac_update(*({k: v.copy() for k, v in p.items()} for p in (actor, critic, critic)), onp.AdamState.zeros_like(actor),
+                          onp.AdamState.zeros_like(critic), batch_from(arrays, idx), eps[0], eps[1], hp)
+    assert abs(float(on32["loss_q"]) - float(on["loss_q"])) > 1e-5                        # the mode changes the numbers ...
+    assert_close(float(ot["loss_q"]), float(on["loss_q"]), 2e-6, 1e-6, "loss_q")           # ... and both restatements agree on them
+    assert_close(float(ot["loss_pi"]), float(on["loss_pi"]), 2e-5, 2e-6, "loss_pi")        # (evaluated after the critic's Adam step)
+
+    def close(got, want, name):                           # fp32 summation order can flip a bf16 rounding downstream: allow a few
+        got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+        err = np.abs(got - want)
+        bad = err > 1e-6 + 1e-4 * np.abs(want)
+        assert bad.mean() <= 0.02 and err.max() <= 1e-2 * np.abs(want).max() + 1e-7, f"{name}: {bad.sum()} / {bad.size} off, max {err.max():.2e}"
+    for n_ in CRITIC_KEYS:
+        close(ot["critic_grads"][n_].numpy(), on["critic_grads"][n_], n_)
+    for n_ in ACTOR_KEYS:
+        close(ot["actor_grads"][n_].numpy(), on["actor_grads"][n_], n_)
