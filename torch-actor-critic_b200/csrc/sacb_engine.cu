@@ -923,6 +923,7 @@ int sacb_comm_init(sacb_handle e, const char* lib, const uint8_t id_in[128], int
     memcpy(id.internal, id_in, 128);
     NC(g_nccl.CommInitRank(&e->comm, world, id, rank));
     e->rank = rank; e->world = world;
+    e->dirty = true;                                   // the phase programs depend on the world size (fused vs separate Adam)
     return 0;
 }
 
