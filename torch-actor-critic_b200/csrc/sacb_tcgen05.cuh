@@ -323,7 +323,8 @@ constexpr int kBfStageBytes = (kBfStageAFloats + kBfStageBFloats) * 4;  // 52,22
 constexpr int kBfOpABytes = kBfM * kBfK * 2, kBfOpBBytes = kBfN * kBfK * 2;
 constexpr int kBfOpOff = 2 * kBfStageBytes;                             // 104,448
 constexpr int kBfEpiOff = kBfOpOff + 2 * (kBfOpABytes + kBfOpBBytes);   // 153,600: bias[64], w2[64]
-constexpr int kBfMaskOff = kBfEpiOff + 2 * kBfN * 4;                    // 154,112: relu-mask tile [128][68] fp32
+constexpr int kBfCntOff = kBfEpiOff + 2 * kBfN * 4;                     // 154,112: arrival counters of the two operand buffers
+constexpr int kBfMaskOff = kBfCntOff + 16;                              // relu-mask tile [128][68] fp32
 static_assert(kBfMaskOff + kBfM * kBfPitchRC * 4 <= kT5PipeBytes, "bf16 tile buffers must fit in the tcgen05 kernel's shared memory");
 static_assert(kBfK * (kBfM + 4) <= kBfStageAFloats && kBfK * (kBfN + 4) <= kBfStageBFloats, "staging holds either layout");
 
@@ -342,29 +343,33 @@ __device__ __forceinline__ unsigned bf_pack(float lo, float hi) {
     return r;
 }
 
-// fp32 operand tile (R outputs x 64 reduction elements from (o0, k0)) -> staging.  RC: [R][68]; OC: [64][R+4].
-// The issue cost of these copies is what bounds a chunk (measured: 12 cp.async per thread cost ~1,300 cycles with
-// per-copy index math), so every thread derives ONE base pointer and walks it with a compile-time stride.
+// The K loop has no block-wide barrier: every warp OWNS a slice of the tile's output rows (A: 16 rows, B: 8 rows; for
+// output-contiguous operands the same slice of columns), stages that slice with its own cp.async groups, converts it and
+// then arrives on a shared-memory counter; the warp that arrives last issues the chunk's MMAs and commits them to the
+// mbarrier that guards the operand buffer.  Nobody waits for a slower warp except through that mbarrier two chunks later.
+//
+// fp32 operand slice of warp w (RW = R/8 outputs x 64 reduction elements from (o0, k0)) -> staging.  RC: [R][68]; OC: [64][R+4].
 template <bool RC, int R>
-__device__ __forceinline__ void bf_stage(float* s, const float* __restrict__ g, int ld, int o0, int o_valid, int k0, int k_valid, int vec) {
+__device__ __forceinline__ void bf_stage_w(float* s, const float* __restrict__ g, int ld, int o0, int o_valid, int k0, int k_valid, int vec) {
     constexpr int P = RC ? kBfPitchRC : R + 4;
-    const int t = threadIdx.x;
+    constexpr int RW = R / (kThreads / 32);                // outputs owned by a warp: 16 (A) / 8 (B)
+    const int lane = threadIdx.x & 31, ow = (threadIdx.x >> 5) * RW;
     if (vec) {
-        if (RC) {                        // thread -> (row t/16 + 16q, 4 k's at (t%16)*4)
-            const int o = t >> 4, r = (t & 15) << 2;
+        if (RC) {                        // lane -> (row ow + lane/16 + 2q, 4 k's at (lane%16)*4)
+            const int o = ow + (lane >> 4), r = (lane & 15) << 2;
             const int nbk = r < k_valid ? min(4, k_valid - r) * 4 : 0;
             const float* src = g + (size_t)(o0 + o) * ld + k0 + r;
             float* dst = s + o * P + r;
-            const size_t step = (size_t)16 * ld;
+            const size_t step = (size_t)2 * ld;
 #pragma unroll
-            for (int q = 0; q < (R * 16) / kThreads; ++q) {
-                const int nb = (o + 16 * q < o_valid) ? nbk : 0;
-                cp_async16(dst + q * 16 * P, nb ? src : g, nb);
+            for (int q = 0; q < RW / 2; ++q) {
+                const int nb = (o + 2 * q < o_valid) ? nbk : 0;
+                cp_async16(dst + q * 2 * P, nb ? src : g, nb);
                 src += step;
             }
-        } else {                         // thread -> (k-row t/VR + (256/VR)q, 4 outputs at (t%VR)*4)
-            constexpr int VR = R / 4, RS = kThreads / VR;
-            const int r = t / VR, o = (t % VR) << 2;
+        } else {                         // lane -> (k-row lane/VW + (32/VW)q, 4 outputs at ow + (lane%VW)*4)
+            constexpr int VW = RW / 4, RS = 32 / VW;       // vectors per k-row of the slice: 4 (A) / 2 (B)
+            const int r = lane / VW, o = ow + ((lane % VW) << 2);
             const int nbo = o < o_valid ? min(4, o_valid - o) * 4 : 0;
             const float* src = g + (size_t)(k0 + r) * ld + o0 + o;
             float* dst = s + r * P + o;
@@ -379,8 +384,8 @@ __device__ __forceinline__ void bf_stage(float* s, const float* __restrict__ g, 
     } else {            // element-wise path for unaligned operands; the reduction tail is zero-filled to a multiple of 16
         const int k_pad = min(kBfK, (k_valid + 15) & ~15);
 #pragma unroll 4
-        for (int e = t; e < R * kBfK; e += kThreads) {
-            const int o = RC ? e >> 6 : e % R, r = RC ? e & 63 : e / R;       // R and 64 are powers of two: shifts
+        for (int e = lane; e < RW * kBfK; e += 32) {
+            const int o = ow + (RC ? e >> 6 : e % RW), r = RC ? e & 63 : e / RW;
             if (o < o_valid && r < k_pad) {
                 float* dst = RC ? s + o * P + r : s + r * P + o;
                 if (r < k_valid) cp_async4(dst, RC ? g + (size_t)(o0 + o) * ld + k0 + r : g + (size_t)(k0 + r) * ld + o0 + o);
@@ -390,14 +395,16 @@ __device__ __forceinline__ void bf_stage(float* s, const float* __restrict__ g, 
     }
 }
 
-// staging (fp32) -> bf16 K-major UMMA tile.  One thread = one 16-byte chunk (8 consecutive k of one output row);
-// consecutive threads take consecutive rows, so a quarter-warp writes one contiguous 128-byte core matrix.
+// staging (fp32) -> bf16 K-major UMMA tile, the warp's own slice.  One lane = one 16-byte chunk (8 consecutive k of one
+// output row); consecutive lanes take consecutive rows, so a quarter-warp writes one contiguous 128-byte core matrix.
 template <bool RC, int R>
-__device__ __forceinline__ void bf_convert(const float* st, char* op, int k_valid) {
+__device__ __forceinline__ void bf_convert_w(const float* st, char* op, int k_valid) {
     constexpr int P = RC ? kBfPitchRC : R + 4;
+    constexpr int RW = R / (kThreads / 32);
     const int nkc = (min(kBfK, (k_valid + 15) & ~15)) >> 3;
-    for (int c = threadIdx.x; c < R * nkc; c += kThreads) {
-        const int o = c % R, kc = c / R;
+    const int lane = threadIdx.x & 31, ow = (threadIdx.x >> 5) * RW;
+    for (int c = lane; c < RW * nkc; c += 32) {
+        const int o = ow + c % RW, kc = c / RW;
         float x[8];
         if (RC) {
             const float4 a = *reinterpret_cast<const float4*>(st + o * P + kc * 8);
@@ -441,8 +448,8 @@ __device__ __forceinline__ void gemm_tile_bf16(const Job& jb, int tile, char* pi
         float* sa = reinterpret_cast<float*>(pipe + (c & 1) * kBfStageBytes);
         float* sb = sa + kBfStageAFloats;
         const int k0 = c * kBfK, kv = min(kBfK, K - k0);
-        bf_stage<A_RC, kBfM>(sa, Ag, jb.lda, i0, i_valid, k0, kv, jb.a_vec);
-        bf_stage<B_RC, kBfN>(sb, Bg, jb.ldb, j0, j_valid, k0, kv, jb.b_vec);
+        bf_stage_w<A_RC, kBfM>(sa, Ag, jb.lda, i0, i_valid, k0, kv, jb.a_vec);
+        bf_stage_w<B_RC, kBfN>(sb, Bg, jb.ldb, j0, j_valid, k0, kv, jb.b_vec);
     };
     issue(0);
     // relu mask of the tile (E_MASK) rides in the first cp.async group: its L2 latency hides behind the K loop
@@ -465,37 +472,44 @@ __device__ __forceinline__ void gemm_tile_bf16(const Job& jb, int tile, char* pi
         const int c = threadIdx.x - kBfN;
         s_w2[c] = (jb.epi == E_BIAS_RELU_DOT && j0 + c < N) ? __ldcg(jb.aux0 + (size_t)z * jb.sAux + j0 + c) : 0.f;
     }
+    int* s_cnt = reinterpret_cast<int*>(pipe + kBfCntOff);
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();                                        // counters zeroed before any warp can arrive
 
     const unsigned idesc = bf_idesc();
+    const int lane = threadIdx.x & 31;
     for (int c = 0; c < nch; ++c) {
         const int b = c & 1;
         const int kv = min(kBfK, K - c * kBfK);
-        TR(200);
-        cp_async_wait<1>();                                 // chunk c has landed (one younger group may be in flight)
-        __syncthreads();
-        TR(201);
-        if (c >= 2) bf_wait(cx, b);
-        TR(202);                         // MMAs of chunk c-2 are done with this operand buffer
+        cp_async_wait<1>();                                 // this lane's copies of chunk c have landed ...
+        __syncwarp();                                       // ... and so have the rest of the warp's slice
+        if (c >= 2) bf_wait(cx, b);                         // MMAs of chunk c-2 are done with this operand buffer
         const float* sa = reinterpret_cast<const float*>(pipe + b * kBfStageBytes);
         char* oa = pipe + kBfOpOff + b * (kBfOpABytes + kBfOpBBytes);
         char* ob = oa + kBfOpABytes;
-        bf_convert<A_RC, kBfM>(sa, oa, kv);
-        bf_convert<B_RC, kBfN>(sa + kBfStageAFloats, ob, kv);
+        bf_convert_w<A_RC, kBfM>(sa, oa, kv);
+        bf_convert_w<B_RC, kBfN>(sa + kBfStageAFloats, ob, kv);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the tensor core
-        __syncthreads();
-        TR(203);
-        if (c + 2 < nch) issue(c + 2);                      // the staging buffer just converted is free again
+        __syncwarp();
+        if (c + 2 < nch) issue(c + 2);                      // the warp's staging slice just converted is free again
         cp_async_commit();
-        TR(204);
-        if (threadIdx.x == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            unsigned long long da = t5_desc(smem_u32(oa), 128u, 1024u, false), db = t5_desc(smem_u32(ob), 128u, 1024u, false);
-            const int nk16 = (kv + 15) >> 4;
-            for (int k16 = 0; k16 < nk16; ++k16) {
-                bf_mma(cx.tmem, da, db, idesc, (c == 0 && k16 == 0) ? 0u : 1u);
-                da += 16; db += 16;                         // two 128-byte chunk columns per K=16 step (16-byte units)
+        if (lane == 0) {
+            __threadfence_block();                          // release: the slice is written (and proxy-fenced) before the arrival
+            const int seen = atomicAdd(&s_cnt[b], 1);
+            if (seen == kThreads / 32 - 1) {                // last warp in: the whole chunk is in place
+                s_cnt[b] = 0;                               // next use is chunk c+2, behind the mbarrier wait on this buffer
+                __threadfence_block();                      // acquire
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                unsigned long long da = t5_desc(smem_u32(oa), 128u, 1024u, false), db = t5_desc(smem_u32(ob), 128u, 1024u, false);
+                const int nk16 = (kv + 15) >> 4;
+                for (int k16 = 0; k16 < nk16; ++k16) {
+                    bf_mma(cx.tmem, da, db, idesc, (c == 0 && k16 == 0) ? 0u : 1u);
+                    da += 16; db += 16;                     // two 128-byte chunk columns per K=16 step (16-byte units)
+                }
+                t5_commit(b ? cx.mbar_op1 : cx.mbar_op0);
+                // the next chunk's MMAs may be issued by another thread (whichever warp arrives last): order them after these
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
-            t5_commit(b ? cx.mbar_op1 : cx.mbar_op0);
         }
     }
     TR(205);
@@ -504,6 +518,7 @@ __device__ __forceinline__ void gemm_tile_bf16(const Job& jb, int tile, char* pi
     if (nch >= 2) bf_wait(cx, (nch - 2) & 1);
     bf_wait(cx, (nch - 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();        // every warp is out of the K loop (the staging buffers become the epilogue's tile buffer)
     TR(206);
 
     // ---- epilogue, two steps so that all 256 threads work and every global access is coalesced (a thread-per-row
