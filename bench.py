@@ -7,16 +7,26 @@ buffer, 1e6 transitions in HBM, obs=17, act=6, MLP 256x256, batch=256, fp32).
 One "step" = one SAC gradient update = sample -> update_critic -> update_policy -> update_targets
 (reference sac/algorithm.py:275-278).  Updates are issued in bursts of update_every=50 (sac/algorithm.py:273-274),
 each burst being one persistent-kernel launch.  N>1: one process per GPU under torchrun, every rank owns an
-independent replay shard (default_rng(rank)) and the critic / actor gradients are NCCL-averaged inside every update
-(weak scaling: batch 256 per GPU).  `value` counts batch-256 gradient updates summed over GPUs (= samples/s / 256);
-`config.global_steps_per_s` is the synchronous optimizer-step rate.
+independent replay shard (default_rng(rank)); the critic / actor gradients are averaged inside every update by the
+engine's in-kernel NVLink exchange (CUDA-IPC peer loads from the other ranks' gradient arenas, fixed rank order;
+`SACB_COMM=nccl` selects ncclAllReduce between launches instead).  torch.distributed/NCCL only carries the barriers,
+the IPC-handle exchange and the initial parameter broadcast.  Weak scaling: batch 256 per GPU.  `value` counts
+batch-256 gradient updates summed over GPUs (= samples/s / 256); `config.global_steps_per_s` is the synchronous
+optimizer-step rate.  After the timed region every rank's parameter checksum is all-reduced (min == max) and reported
+as `config.replicas_identical`.
 
-`--impl reference` times the CPU arm: the torch-CPU port of the reference's hot loop (oracle/sac_torch_cpu.py; the
-reference tree itself is Python under /root/reference and does not exist on the GPU box) on the same synthetic
-arrays, on the host cores.
+The same JSON line carries `config.extra_workloads.c2`: BASELINE configs[2] (Humanoid-shaped, obs=376, act=17,
+MLP 512x512, batch=1024, bf16 tensor-core MLP path) measured at N=1 right after the C1 numbers.
+
+`--impl reference` times the CPU arm: the UNMODIFIED reference (oracle/_ref, a verbatim copy made by
+oracle/build_ref.py; the reference tree itself does not exist on the GPU box) running
+ReplayBuffer.sample -> SAC.update_critic -> SAC.update_policy -> update_targets on the same synthetic arrays on
+the host cores at the reference's own 2 torch threads (main.py:130).  Falls back to the torch-CPU port
+(oracle/sac_torch_cpu.py, kind "port") only when oracle/_ref is absent.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -28,32 +38,47 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-O, A, H, B, N_BUF, UPDATE_EVERY = 17, 6, [256, 256], 256, 1_000_000, 50
-P_ACTOR, P_CRITIC = 73_484, 144_386
-# algorithmic work per update (SURVEY.md section 8d / BASELINE.md section 4)
-BYTES_PER_UPDATE = B * (2 * O + A + 2) * 4 + 28 * (P_ACTOR + P_CRITIC) + 12 * P_CRITIC     # 7,876,000
-A_F = O * 256 + 256 * 256 + 2 * 256 * A
-C_F = (O + A) * 256 + 256 * 256 + 256
-FLOPS_PER_UPDATE = 2 * B * (3 * A_F + 10 * C_F + 3 * 256 * 256 + 2 * 256 + 2 * 256 * A)   # 581.6 MFLOP
+UPDATE_EVERY = 50
 METRIC = "SAC gradient-updates/sec (batch=256, MLP 256x256)"
 UNIT = "updates/s"
-WORKLOAD = "HalfCheetah-shaped synthetic replay (obs=17, act=6, 1e6 transitions), MLP 256x256, batch=256, fp32"
 
 
-def synth_buffer(rank, n=N_BUF):
-    """states/next_states ~ N(0,1), actions ~ U(-1,1), rewards ~ N(0,1), done ~ Bernoulli(1e-3)."""
-    rng = np.random.default_rng(rank)
-    return dict(state=rng.standard_normal((n, O), dtype=np.float32), actions=rng.uniform(-1, 1, (n, A)).astype(np.float32),
-                rewards=rng.standard_normal(n, dtype=np.float32), next_state=rng.standard_normal((n, O), dtype=np.float32),
-                done=rng.random(n) < 1e-3)
+class Workload:
+    def __init__(self, name):
+        self.name = name
+        if name == "c1":
+            self.O, self.A, self.H, self.B, self.N, self.act_limit = 17, 6, [256, 256], 256, 1_000_000, 1.0
+            self.label = "HalfCheetah-shaped synthetic replay (obs=17, act=6, 1e6 transitions), MLP 256x256, batch=256, fp32"
+        elif name == "c2":
+            self.O, self.A, self.H, self.B, self.N, self.act_limit = 376, 17, [512, 512], 1024, 200_000, 0.4
+            self.label = "Humanoid-shaped synthetic replay (obs=376, act=17, 2e5 transitions), MLP 512x512, batch=1024, bf16 tensor-core MLP path"
+        else:
+            raise ValueError(name)
+        O, A, (H1, H2), B = self.O, self.A, self.H, self.B
+        self.p_actor = H1 * O + H1 + H2 * H1 + H2 + 2 * (A * H2 + A)
+        self.p_critic = 2 * (H1 * (O + A) + H1 + H2 * H1 + H2 + H2 + 1)
+        # algorithmic work per update (SURVEY.md section 8d / BASELINE.md section 4)
+        self.bytes_per_update = B * (2 * O + A + 2) * 4 + 28 * (self.p_actor + self.p_critic) + 12 * self.p_critic
+        a_f = O * H1 + H1 * H2 + 2 * H2 * A
+        c_f = (O + A) * H1 + H1 * H2 + H2
+        self.flops_per_update = 2 * B * (3 * a_f + 10 * c_f + 3 * H1 * H2 + 2 * H2 + 2 * H2 * A)
+
+    def synth(self, rank):
+        """states/next_states ~ N(0,1), actions ~ U(-1,1), rewards ~ N(0,1), done ~ Bernoulli(1e-3)."""
+        rng = np.random.default_rng(rank)
+        n, O, A = self.N, self.O, self.A
+        return dict(state=rng.standard_normal((n, O), dtype=np.float32), actions=rng.uniform(-1, 1, (n, A)).astype(np.float32),
+                    rewards=rng.standard_normal(n, dtype=np.float32), next_state=rng.standard_normal((n, O), dtype=np.float32),
+                    done=rng.random(n) < 1e-3)
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+        return dict(hbm=float(d["hbm_gbs"]), tensor=float(d.get("bf16_tflops", 1590.0)),
+                    tensor_sustained=float(d.get("bf16_tflops_sustained", 1400.0)), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -66,7 +91,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -79,7 +104,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -95,32 +120,41 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_rate(arrays, threads, n_updates, warmup, max_seconds):
-    """updates/s of the torch-CPU port of sac/algorithm.py:274-281 on the host (oracle = checker / baseline only).
-    Bounded: stops after `max_seconds` of timed work."""
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference itself (oracle/_ref), or the torch-CPU port when that copy is absent
+# ----------------------------------------------------------------------------------------------------------------
+REF_THREADS = 2          # the reference's own setting, main.py:130 `torch.set_num_threads(2)`
+
+
+def cpu_rate(wl, arrays, threads, n_updates, warmup, max_seconds):
+    """(updates/s, updates timed, kind) of the reference hot loop on the host.  oracle/ is the checker / baseline only."""
+    from oracle import build_ref
+    if build_ref.available() or build_ref.build(quiet=True):
+        from oracle.ref_runner import reference_rate
+        rate, done = reference_rate(arrays, wl.O, wl.A, wl.H, wl.B, wl.act_limit, threads, n_updates, warmup, max_seconds)
+        return rate, done, "reference"
     import torch
     from oracle.sac_numpy import HyperParams, init_params
     from oracle.sac_torch_cpu import HostReplay, TorchCpuSAC, time_cpu_updates
     torch.set_num_threads(threads)
-    actor, critic = init_params(O, A, H, np.random.default_rng(0))
-    sac = TorchCpuSAC(actor, critic, HyperParams(act_limit=1.0))
+    actor, critic = init_params(wl.O, wl.A, wl.H, np.random.default_rng(0))
+    sac = TorchCpuSAC(actor, critic, HyperParams(act_limit=wl.act_limit))
     replay = HostReplay(arrays["state"], arrays["actions"], arrays["rewards"], arrays["next_state"], arrays["done"])
-    dt, done = time_cpu_updates(replay, sac, B, n_updates, warmup, UPDATE_EVERY, max_seconds=max_seconds)
-    return done / dt, done
+    dt, done = time_cpu_updates(replay, sac, wl.B, n_updates, warmup, UPDATE_EVERY, max_seconds=max_seconds)
+    return done / dt, done, "port"
 
 
-def cpu_baseline(arrays, steps, warmup, budget_s):
-    """Best thread count among 1, 2 (the reference's own setting, main.py:130), 8, 16, 32 (<= host cores): the update is a
-    chain of tiny GEMMs, so more threads stop helping early and oversubscription hurts.  Short probes pick the thread
-    count, then the bounded sample runs at it."""
+def cpu_arm(wl, arrays, n_updates, warmup, budget_s, probe_threads):
+    """The headline CPU number is taken at the reference's own thread count (2) over >= n_updates updates (steady:
+    the spread across runs is the box, not a thread-count lottery); other thread counts are short probes reported
+    beside it."""
     cores = os.cpu_count() or 1
-    cands = sorted({t for t in (1, 2, 8, 16, 32) if t <= cores})
+    rate, done, kind = cpu_rate(wl, arrays, REF_THREADS, n_updates, warmup, budget_s)
     probe = {}
-    for t in cands:
-        probe[t] = round(cpu_port_rate(arrays, t, 40, 5, budget_s / (4 * len(cands)))[0], 2)
-    best = max(probe, key=probe.get)
-    rate, done = cpu_port_rate(arrays, best, steps, warmup, budget_s / 2)
-    return rate, best, done, probe, cores
+    for t in probe_threads:
+        if t <= cores and t != REF_THREADS:
+            probe[t] = round(cpu_rate(wl, arrays, t, 60, 5, budget_s / 8)[0], 2)
+    return rate, done, kind, probe, cores
 
 
 def run_reference(args):
@@ -128,24 +162,138 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    arrays = synth_buffer(0)
-    rate, thr, done, probe, cores = cpu_baseline(arrays, max(1, args.steps), max(3, min(args.warmup, 50)), budget_s=60.0)
-    sample = (f"{done} updates (bursts of {UPDATE_EVERY}) timed at {thr} torch threads after warm-up, torch {torch.__version__} CPU; "
-              f"thread probe (updates/s) {probe}; host cpu_count={cores}")
+    wl = Workload(args.workload)
+    arrays = wl.synth(0)
+    # always >= 300 timed updates whatever --steps is (a 20-update sample swings +-10 %), seconds-bounded
+    n = max(300, args.steps)
+    warm = max(20, min(args.warmup, 50))
+    rate, done, kind, probe, cores = cpu_arm(wl, arrays, n, warm, budget_s=90.0, probe_threads=(1, 8, 32))
+    what = ("the UNMODIFIED reference (oracle/_ref): ReplayBuffer.sample -> SAC.update_critic -> SAC.update_policy -> update_targets"
+            if kind == "reference" else "torch-CPU port of the reference loop (oracle/_ref absent)")
+    sample = (f"{done} updates of {what}, timed at {REF_THREADS} torch threads (the reference's own setting, main.py:130) after "
+              f"{warm} warm-up updates, torch {torch.__version__} CPU; other thread counts (60-update probes, updates/s): {probe}; "
+              f"host cpu_count={cores}")
     line = {"impl": "reference", "metric": METRIC, "value": round(rate, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-            "warmup": max(3, min(args.warmup, 50)), "ms_per_step": round(1000.0 / rate, 4), "higher_is_better": True,
+            "warmup": warm, "ms_per_step": round(1000.0 / rate, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "update_every": UPDATE_EVERY, "host_cpu_count": cores},
-            "cpu_baseline": {"value": round(rate, 2), "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
+            "config": {"workload": wl.label, "update_every": UPDATE_EVERY, "host_cpu_count": cores, "threads": REF_THREADS,
+                       "thread_probe_updates_per_s": probe},
+            "cpu_baseline": {"value": round(rate, 2), "unit": UNIT, "cores": REF_THREADS, "kind": kind, "sample": sample},
             "e2e": {"value": round(rate, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+GEMM_ARITH = {0: "fp32 FFMA", 1: "tensor-core 3xTF32 via mma.sync (fp32-level accuracy), fp32 accumulate",
+              2: "tensor-core 3xTF32 via tcgen05/TMEM (fp32-level accuracy), fp32 accumulate",
+              3: "tcgen05 bf16 operands, fp32 accumulate in TMEM, fp32 master weights/Adam"}
+
+
+class Rig:
+    """One SAC training set-up (modules, optimizers, HBM replay ring) for a workload on this rank's GPU."""
+
+    def __init__(self, wl, rank, local, precision, mode):
+        import torch
+        import torch.optim as optim
+        from copy import deepcopy
+        from torch_actor_critic_b200.buffer.replay_buffer import ReplayBuffer
+        from torch_actor_critic_b200.networks.linear import Actor, DoubleCritic
+        from torch_actor_critic_b200.sac.algorithm import SAC
+        from torch_actor_critic_b200.sac.mpi import sync_params
+        self.wl, self.torch = wl, torch
+        self.arrays = wl.synth(rank)
+        torch.manual_seed(0)
+        self.actor = Actor(wl.O, wl.A, wl.H, act_limit=wl.act_limit, device=local)
+        self.critic = DoubleCritic(wl.O, wl.A, wl.H, device=local)
+        self.target = deepcopy(self.critic)
+        sync_params(self.actor); sync_params(self.critic); sync_params(self.target)
+        self.pi_opt = optim.Adam(self.actor.parameters(), lr=3e-4)
+        self.q_opt = optim.Adam(self.critic.parameters(), lr=3e-4)
+        self.sac = SAC(alpha=0.2, gamma=0.99, polyak=0.995, reward_scale=1.0, epochs=1, batch_size=wl.B, start_steps=0,
+                       steps_per_epoch=1, max_ep_len=1000, update_after=0, update_every=UPDATE_EVERY, save_every=1)
+        self.sac.seed = 10000 * rank                                   # sac/algorithm.py:203
+        self.buf = ReplayBuffer(wl.N, wl.O, wl.A, device=local, seed=10000 * rank)
+        a = self.arrays
+        self.buf.store_many(a["state"], a["actions"], a["rewards"], a["next_state"], a["done"])
+        self.eng = self.sac._engine(self.actor, self.critic, wl.B, target=self.target, pi_opt=self.pi_opt, q_opt=self.q_opt)
+        self.eng.set_mode(mode)
+        self.eng.set_precision(precision)
+        torch.cuda.synchronize()
+        self.cursor = 0
+
+    def burst(self, n):
+        return self.sac.update_burst(n, self.actor, self.critic, self.target, self.buf, self.pi_opt, self.q_opt)
+
+    def run_updates(self, total, with_host_io):
+        """`total` updates in bursts of UPDATE_EVERY.  with_host_io: the reference training loop's host traffic --
+        before each burst the update_every new transitions go host->HBM (ReplayBuffer.store, pinned staging inside
+        sacb_store), after it the 2 x n losses come back (sac/algorithm.py:280-281)."""
+        done, last, a, N = 0, None, self.arrays, self.wl.N
+        while done < total:
+            n = min(UPDATE_EVERY, total - done)
+            if with_host_io:
+                for i in range(n):
+                    j = (self.cursor + i) % N
+                    self.buf.store(a["state"][j], a["actions"][j], a["rewards"][j], a["next_state"][j], a["done"][j])
+                self.cursor += n
+            lq, lp = self.burst(n)
+            if with_host_io:
+                last = (lq.cpu(), lp.cpu())
+            done += n
+        return last
+
+    def checksum(self):
+        """Order-independent integer checksum of every replicated parameter / optimizer arena (bit pattern sums)."""
+        t = self.torch
+        ent = self.sac._entry(self.actor, self.critic, self.wl.B)
+        parts = [self.actor.arena, self.critic.arena, self.target.arena, ent["pi"].m, ent["pi"].v, ent["q"].m, ent["q"].v]
+        return t.stack([p.view(t.int32).to(t.int64).sum() for p in parts])
+
+
+def timed_region(rig, steps, with_host_io, world, repeats):
+    """Times EXACTLY `steps` updates between barrier + synchronize on both sides, CUDA events on the launch stream, max over
+    ranks; repeated `repeats` times (each repeat is its own K-step measurement) and the median is reported."""
+    import torch
+    import torch.distributed as dist
+    out = []
+    for _ in range(repeats):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        rig.run_updates(steps, with_host_io)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), wall * 1e3 if with_host_io else 0.0)     # host I/O arm: wall clock dominates
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        out.append(ms)
+    return float(np.median(out)), out
+
+
+def kernel_ms(rig, n=8):
+    """Dominant kernel (the persistent sac_phase_kernel): CUDA events around single full bursts on the launch stream."""
+    import torch
+    kms = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); rig.burst(UPDATE_EVERY); e1.record(); torch.cuda.synchronize()
+        kms.append(e0.elapsed_time(e1))
+    return float(np.mean(kms))
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    import torch.optim as optim
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -163,147 +311,103 @@ def run_gpu(args):
         ge.build()
     if world > 1:
         dist.barrier()
-    from torch_actor_critic_b200.buffer.replay_buffer import ReplayBuffer
-    from torch_actor_critic_b200.networks.linear import Actor, DoubleCritic
-    from torch_actor_critic_b200.sac.algorithm import SAC
-    from torch_actor_critic_b200.sac.mpi import sync_params
-    from copy import deepcopy
 
-    arrays = synth_buffer(rank)
-    torch.manual_seed(0)
-    actor = Actor(O, A, H, act_limit=1.0 if args.workload == 'c1' else 0.4, device=local)
-    critic = DoubleCritic(O, A, H, device=local)
-    target = deepcopy(critic)
-    sync_params(actor); sync_params(critic); sync_params(target)
-    pi_opt = optim.Adam(actor.parameters(), lr=3e-4)
-    q_opt = optim.Adam(critic.parameters(), lr=3e-4)
-    sac = SAC(alpha=0.2, gamma=0.99, polyak=0.995, reward_scale=1.0, epochs=1, batch_size=B, start_steps=0,
-              steps_per_epoch=1, max_ep_len=1000, update_after=0, update_every=UPDATE_EVERY, save_every=1)
-    sac.seed = 10000 * rank                                        # sac/algorithm.py:203
-    buf = ReplayBuffer(N_BUF, O, A, device=local, seed=10000 * rank)
-    buf.store_many(arrays["state"], arrays["actions"], arrays["rewards"], arrays["next_state"], arrays["done"])
+    wl = Workload(args.workload)
+    precision = args.precision if args.precision >= 0 else (3 if wl.name == "c2" else 1)
+    rig = Rig(wl, rank, local, precision, args.mode)
+    eng = rig.eng
+    rig.run_updates(args.warmup, False)                             # W untimed warm-up steps
     torch.cuda.synchronize()
-
-    def burst(n):
-        return sac.update_burst(n, actor, critic, target, buf, pi_opt, q_opt)
-
-    def run_updates(total, with_host_io):
-        """`total` updates in bursts of UPDATE_EVERY.  with_host_io: the reference training loop's host traffic --
-        before each burst the update_every new transitions go host->HBM (ReplayBuffer.store, pinned staging inside
-        sacb_store), after it the 2 x n losses come back (sac/algorithm.py:280-281)."""
-        done, cursor, last = 0, 0, None
-        while done < total:
-            n = min(UPDATE_EVERY, total - done)
-            if with_host_io:
-                for i in range(n):
-                    j = (cursor + i) % N_BUF
-                    buf.store(arrays["state"][j], arrays["actions"][j], arrays["rewards"][j], arrays["next_state"][j],
-                              arrays["done"][j])
-                cursor += n
-            lq, lp = burst(n)
-            if with_host_io:
-                last = (lq.cpu(), lp.cpu())
-            done += n
-        return last
-
-    def timed(total, with_host_io):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record()
-        run_updates(total, with_host_io)
-        e1.record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        ms = max(e0.elapsed_time(e1), wall * 1e3 if with_host_io else 0.0)     # host I/O arm: wall clock dominates
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            dist.barrier()
-        return ms
-
-    eng = sac._engine(actor, critic, B, target=target, pi_opt=pi_opt, q_opt=q_opt)
-    eng.set_mode(args.mode)
-    eng.set_precision(args.precision)
-    run_updates(args.warmup, False)                                 # W untimed warm-up steps
-    torch.cuda.synchronize()
+    # each repeat times exactly K steps; enough repeats that the clocks sampler sees the GPU under load
+    repeats = args.repeats if args.repeats > 0 else max(1, min(40, math.ceil(4000 / max(args.steps, 1))))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count()
-    ms = timed(args.steps, False)                                   # EXACTLY K timed steps, inputs resident in HBM
-    launches = eng.launch_count() - l0
+    ms, ms_all = timed_region(rig, args.steps, False, world, repeats)      # inputs resident in HBM
+    launches = (eng.launch_count() - l0) // repeats
     clocks = sampler.stop() if rank == 0 else None
-    run_updates(min(args.warmup, 2 * UPDATE_EVERY), True)
-    ms_e2e = timed(args.steps, True)
+    rig.run_updates(min(args.warmup, 2 * UPDATE_EVERY), True)
+    ms_e2e, _ = timed_region(rig, args.steps, True, world, max(1, min(repeats, 10)))
+    k_ms = kernel_ms(rig)
 
-    # dominant kernel (the persistent sac_phase_kernel): CUDA events around single full bursts on the launch stream
-    kms = []
-    for _ in range(8):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); burst(UPDATE_EVERY); e1.record(); torch.cuda.synchronize()
-        kms.append(e0.elapsed_time(e1))
-    k_ms = float(np.mean(kms))
+    replicas_identical = None
+    if world > 1:
+        cs = rig.checksum()
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replicas_identical = bool(torch.equal(lo, hi))
 
     if rank != 0:
         return
-    hbm_peak, tensor_peak, peak_src = peaks()
+    pk = peaks()
     upd_per_launch = UPDATE_EVERY
-    ach = BYTES_PER_UPDATE * upd_per_launch / (k_ms * 1e-3) / 1e9
+    ach = wl.bytes_per_update * upd_per_launch / (k_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch") if args.workload == "c1" else None
+    if os.path.exists(tp) and wl.name == "c1":
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     value = world * args.steps / (ms * 1e-3)
     e2e_v = world * args.steps / (ms_e2e * 1e-3)
+    O, A, B = wl.O, wl.A, wl.B
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 6), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == 3 else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "update_every": UPDATE_EVERY, "batch_per_gpu": B,
-                   "gemm_arithmetic": GEMM_ARITH[args.precision], "global_batch": B * world,
+        "dtype": "bf16" if precision == 3 else "f32", "data": "synthetic",
+        "config": {"workload": wl.label, "update_every": UPDATE_EVERY, "batch_per_gpu": B,
+                   "gemm_arithmetic": GEMM_ARITH[precision], "global_batch": B * world,
                    "parallelism": f"dp{world}", "global_steps_per_s": round(args.steps / (ms * 1e-3), 1),
                    "samples_per_s": round(value * B, 1),
-                   "l2_policy": f"inputs larger than L2: {N_BUF * ((2 * O + A + 1) * 4 + 1) / 1e6:.0f} MB replay ring, random-row gather; the "
-                                f"{(P_ACTOR + P_CRITIC) * 12 / 1e6 + P_CRITIC * 4 / 1e6:.1f} MB of weights/Adam state is the algorithm's "
+                   "timing": f"median of {repeats} repeats, each EXACTLY {args.steps} steps between barrier+synchronize, CUDA events, max over ranks",
+                   "ms_repeats_min_max": [round(min(ms_all), 4), round(max(ms_all), 4)],
+                   "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                         "in-kernel NVLink peer loads (CUDA IPC), fixed rank order" if os.environ.get("SACB_COMM", "peer") == "peer"
+                                         else "ncclAllReduce between launches"),
+                   "replicas_identical": replicas_identical,
+                   "l2_policy": f"inputs larger than L2: {wl.N * ((2 * O + A + 1) * 4 + 1) / 1e6:.0f} MB replay ring, random-row gather; the "
+                                f"{(wl.p_actor + wl.p_critic) * 12 / 1e6 + wl.p_critic * 4 / 1e6:.1f} MB of weights/Adam state is the algorithm's "
                                 "working set and stays L2-resident by design",
                    "value_definition": f"batch-{B} gradient updates summed over GPUs"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_v, 1), "unit": UNIT, "h2d_bytes_per_step": (2 * O + A + 1) * 4 + 1, "d2h_bytes_per_step": 8,
                 "path": "ReplayBuffer.store (host rows -> pinned staging -> HBM ring) + SAC.update_burst + loss readback per burst"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": round(ach, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 5),
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "sac_phase_kernel (persistent, 50 updates/launch)",
-                     "kernel_ms_per_launch": round(k_ms, 4), "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * upd_per_launch,
-                     "flops": {"achieved_tflops": round(FLOPS_PER_UPDATE * upd_per_launch / (k_ms * 1e-3) / 1e12, 3),
-                               "note": "latency-bound dependency chain of ~18 grid-synchronised phases per update"}},
+        "roofline": {"bound": "hbm", "achieved": round(ach, 2), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 5),
+                     "traffic": traffic, "peak_source": pk["src"], "kernel": "sac_phase_kernel (persistent, 50 updates/launch)",
+                     "kernel_ms_per_launch": round(k_ms, 4), "algorithmic_bytes_per_launch": wl.bytes_per_update * upd_per_launch,
+                     "flops": {"achieved_tflops": round(wl.flops_per_update * upd_per_launch / (k_ms * 1e-3) / 1e12, 3),
+                               "note": "latency-bound dependency chain of grid-synchronised phases per update"}},
     }
+    if world == 1 and wl.name == "c1" and not args.no_extra:
+        # BASELINE configs[2] in front of the driver: Humanoid-shaped, bf16 tensor-core MLP path, same run, same box
+        del rig
+        torch.cuda.empty_cache()
+        try:
+            w2 = Workload("c2")
+            rig2 = Rig(w2, 0, local, 3, 0)
+            rig2.run_updates(100, False)
+            sam2 = ClockSampler(local); sam2.start()
+            ms2, ms2_all = timed_region(rig2, 200, False, 1, 5)
+            clocks2 = sam2.stop()
+            k2 = kernel_ms(rig2, 4)
+            tf = w2.flops_per_update * UPDATE_EVERY / (k2 * 1e-3) / 1e12
+            line["config"]["extra_workloads"] = {"c2": {
+                "workload": w2.label, "value": round(200 / (ms2 * 1e-3), 1), "unit": UNIT, "steps": 200, "warmup": 100,
+                "ms_per_step": round(ms2 / 200, 6), "dtype": "bf16", "gemm_arithmetic": GEMM_ARITH[3],
+                "roofline": {"bound": "tensor", "achieved": round(tf, 2), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                             "frac": round(tf / pk["tensor_sustained"], 5), "peak_source": pk["src"] + " bf16_tflops_sustained",
+                             "kernel_ms_per_launch": round(k2, 4), "flops_per_update": w2.flops_per_update},
+                "clocks": clocks2}}
+            del rig2
+        except Exception as ex:                                       # never lose the C1 line to the side measurement
+            line["config"]["extra_workloads"] = {"c2": {"error": f"{type(ex).__name__}: {ex}"}}
     if world == 1 and not args.no_cpu:
-        rate, thr, done, probe, cores = cpu_baseline(arrays, 600, 20, budget_s=30.0)
-        line["cpu_baseline"] = {"value": round(rate, 2), "unit": UNIT, "cores": thr, "kind": "port",
-                                "sample": f"{done} updates at {thr} torch threads on the same synthetic arrays; thread probe "
-                                          f"(updates/s) {probe}; host cpu_count={cores}"}
+        arrays = wl.synth(0)
+        rate, done, kind, probe, cores = cpu_arm(wl, arrays, 300, 20, budget_s=25.0, probe_threads=())
+        line["cpu_baseline"] = {"value": round(rate, 2), "unit": UNIT, "cores": REF_THREADS, "kind": kind,
+                                "sample": f"{done} updates of the {'unmodified reference (oracle/_ref)' if kind == 'reference' else 'torch-CPU port'} "
+                                          f"at {REF_THREADS} torch threads (main.py:130) on the same synthetic arrays; host cpu_count={cores}"}
     print(json.dumps(line), flush=True)
-
-
-GEMM_ARITH = {0: "fp32 FFMA", 1: "tensor-core 3xTF32 via mma.sync (fp32-level accuracy), fp32 accumulate",
-              2: "tensor-core 3xTF32 via tcgen05/TMEM (fp32-level accuracy), fp32 accumulate",
-              3: "tcgen05 bf16 operands (rounded from fp32 on load), fp32 accumulate in TMEM, fp32 master weights/activations/Adam"}
-
-
-def set_workload(name):
-    global O, A, H, B, N_BUF, P_ACTOR, P_CRITIC, BYTES_PER_UPDATE, FLOPS_PER_UPDATE, WORKLOAD
-    if name == "c2":
-        O, A, H, B, N_BUF = 376, 17, [512, 512], 1024, 200_000
-        P_ACTOR, P_CRITIC = 473_122, 929_794
-        BYTES_PER_UPDATE = B * (2 * O + A + 2) * 4 + 28 * (P_ACTOR + P_CRITIC) + 12 * P_CRITIC
-        a_f = O * 512 + 512 * 512 + 2 * 512 * A
-        c_f = (O + A) * 512 + 512 * 512 + 512
-        FLOPS_PER_UPDATE = 2 * B * (3 * a_f + 10 * c_f + 3 * 512 * 512 + 2 * 512 + 2 * 512 * A)
-        WORKLOAD = "Humanoid-shaped synthetic replay (obs=376, act=17, 2e5 transitions), MLP 512x512, batch=1024, fp32 storage"
 
 
 def main():
@@ -312,16 +416,17 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--repeats", type=int, default=0, help="K-step measurements taken (median reported); 0 = auto")
     ap.add_argument("--mode", type=int, default=0, help="profiling only: 1 = one kernel launch per phase")
     ap.add_argument("--no-cpu", action="store_true", help="profiling only: skip the cpu_baseline leg")
-    ap.add_argument("--precision", type=int, default=1, help="1 = mma.sync 3xTF32 GEMMs (default), 0 = fp32 FFMA, 2 = tcgen05 3xTF32, 3 = tcgen05 bf16 operands")
+    ap.add_argument("--no-extra", action="store_true", help="profiling only: skip the configs[2] side measurement")
+    ap.add_argument("--precision", type=int, default=-1,
+                    help="-1 = workload default (c1: 1, c2: 3); 1 = mma.sync 3xTF32 GEMMs, 0 = fp32 FFMA, 2 = tcgen05 3xTF32, 3 = tcgen05 bf16 operands")
     ap.add_argument("--workload", default="c1", choices=["c1", "c2"],
-                    help="c1 = BASELINE metric workload (default); c2 = Humanoid-shaped (obs=376, act=17, MLP 512x512, batch=1024), "
-                         "fp32 storage -- side measurement only, not the bench line the driver reads")
+                    help="c1 = BASELINE metric workload (default); c2 = Humanoid-shaped (obs=376, act=17, MLP 512x512, batch=1024)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    set_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -35,10 +35,16 @@ typedef enum {
     SACB_ERR_CUDA = -2,      /* CUDA runtime error (message has the detail) */
     SACB_ERR_STATE = -3,     /* call out of order (e.g. update before bind)  */
     SACB_ERR_SAMPLE = -4,    /* sample larger than population (reference: ValueError, replay_buffer.py:46) */
-    SACB_ERR_NCCL = -5
+    SACB_ERR_NCCL = -5,
+    SACB_ERR_PEER = -6       /* in-kernel gradient exchange timed out on a dead / stalled rank (reference: a blocking
+                                comm.recv that never returns, sac/algorithm.py:264-265) */
 } sacb_status;
 
-/* quirk switches.  Default 0 = reproduce the reference exactly. */
+/* quirk switches.  Default 0 = reproduce the reference on one rank exactly.  One INTENTIONAL
+ * deviation with world > 1: the default averages the actor gradient across ranks (the reference's evident intent; it
+ * calls mpi_avg_grads(actor) BEFORE backward(), sac/algorithm.py:155-156, so it effectively never does).
+ * SACB_FLAG_NO_ACTOR_GRAD_SYNC reproduces the reference's behaviour; it needs the NCCL transport (SACB_COMM=nccl),
+ * because the in-kernel peer exchange relies on both exchanges per update to interlock the ranks. */
 #define SACB_FLAG_CANONICAL_LOGPROB 1u   /* 2*(ln2-u-softplus(-2u)) instead of networks/linear.py:51 as written   */
 #define SACB_FLAG_PI_FROM_STATES    2u   /* policy at `states` instead of `next_states` (sac/algorithm.py:37,148-153) */
 #define SACB_FLAG_NO_ACTOR_GRAD_SYNC 4u  /* multi-rank: skip the actor allreduce, as the reference effectively does
@@ -163,6 +169,11 @@ int sacb_sync_params(sacb_handle h, uintptr_t stream);
  * sacb_comm_init may still be used next to it for sacb_sync_params. */
 int sacb_peer_export(sacb_handle h, uint8_t handle_out[64], int64_t* ws_floats);
 int sacb_peer_bind(sacb_handle h, const uint8_t* handles, int32_t rank, int32_t world);
+/* Health of the peer exchange: a waiter that sees no progress for SACB_PEER_TIMEOUT_MS (environment, default 20000)
+ * raises an abort word and every waiter of the launch stops waiting, so a dead rank cannot hang its peers forever
+ * (the reference's blocking comm.recv, sac/algorithm.py:264-265, would).  Synchronises `stream`, then returns 0 or
+ * SACB_ERR_PEER (the message names the missing rank); after a timeout sacb_update refuses further bursts. */
+int sacb_peer_status(sacb_handle h, uintptr_t stream);
 
 /* Test / debug: copy an internal f32 array to HOST memory (synchronous).  Names: "backup","q1","q2","q1_target",
  * "q2_target","a2","logp_next","pi","logp_pi","q1_pi","q2_pi","grad_actor","grad_critic","loss_q_parts", ...

@@ -27,27 +27,11 @@ import torch
 REF = "/root/reference"
 
 
+from oracle.ref_stubs import install_stubs as _install_stubs
+
+
 def install_stubs():
-    def stub(name, **attrs):
-        m = types.ModuleType(name)
-        m.__dict__.update(attrs)
-        sys.modules[name] = m
-        return m
-
-    stub("gym", Env=object)
-    ml = stub("mlflow")
-    ml.pytorch = stub("mlflow.pytorch")
-
-    class _Comm:
-        def Get_rank(self):
-            return 0
-
-        def Get_size(self):
-            return 1
-
-    mpi = types.SimpleNamespace(COMM_WORLD=_Comm(), SUM=0, MIN=1, MAX=2)
-    stub("mpi4py", MPI=mpi)
-    stub("mpi4py.MPI", **mpi.__dict__)
+    _install_stubs()
     if REF not in sys.path:
         sys.path.insert(0, REF)
 

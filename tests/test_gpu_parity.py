@@ -573,3 +573,94 @@ def test_acting_path_cluster_kernel_matches_oracle(n):
     assert not torch.equal(p1, p2) and float(p1.abs().max()) <= 1.0
     pn, none = actor(torch.tensor(x), deterministic=True, with_logprob=False)
     assert none is None and torch.equal(pn, ps)
+
+
+@pytest.mark.parametrize("name,mode", [("small", 0), ("ragged", 0), ("small", 1)])
+def test_pi_from_states_flag_matches_oracle(name, mode):
+    """SACB_FLAG_PI_FROM_STATES: the canonical actor loss pi = actor(states) (the reference evaluates the policy at
+    next_states, sac/algorithm.py:37).  A K-step trajectory against the float64 oracle with pi_from_next_states=False,
+    and the piecewise update_policy program."""
+    from torch_actor_critic_b200 import _lib
+    g, actor, critic, arrays, hp = load_case(name)
+    hp.pi_from_next_states = False
+    K = int(g["n_updates"])
+    eng, av, cv, tv, adam = _engine_for(g, actor, critic, arrays, hp, flags=_lib.FLAG_PI_FROM_STATES)
+    eng.set_mode(mode)
+    lq, lp = eng.update(K, idx=g["idx"], eps=g["eps"])
+    a64, c64, t64 = (onp.cast_params(p, np.float64) for p in (actor, critic, critic))
+    oa, oq = onp.AdamState.zeros_like(a64), onp.AdamState.zeros_like(c64)
+    rq, rp = [], []
+    for k in range(K):
+        o = onp.sac_update(a64, c64, t64, oa, oq, batch_from(arrays, g["idx"][k], np.float64), g["eps"][k, 0].astype(np.float64),
+                           g["eps"][k, 1].astype(np.float64), hp)
+        rq.append(o["loss_q"]); rp.append(o["loss_pi"])
+    assert_close(lq.cpu().numpy(), rq, 1e-3, 1e-4, "loss_q")
+    assert_close(lp.cpu().numpy(), rp, 1e-3, 1e-4, "loss_pi")
+    for k in ACTOR_KEYS:
+        assert_close(av[k].cpu().numpy(), a64[k], 1e-5, 3e-4 * K, f"actor {k}")
+    for k in CRITIC_KEYS:
+        assert_close(cv[k].cpu().numpy(), c64[k], 1e-5, 3e-4 * K, f"critic {k}")
+    assert abs(float(lp[0]) - float(g["loss_pi"][0])) > 1e-4        # it does differ from the reference's pi(next_states)
+
+
+def test_burst_longer_than_one_launch_is_split():
+    """update_every > 64 (e.g. 100, accepted by the reference): Engine.update splits the burst into launches of <= 64
+    updates; the Adam step counters carry across, so the result equals the same updates issued one by one."""
+    g, actor, critic, arrays, hp = load_case("small")
+    B, A = int(g["batch"]), int(g["act_dim"])
+    n, K = len(arrays["rewards"]), 70
+    rng = np.random.default_rng(3)
+    idx = np.stack([rng.choice(n, B, replace=False) for _ in range(K)])
+    eps = rng.standard_normal((K, 2, B, A)).astype(np.float32)
+    outs = []
+    for chunk in (K, 1):
+        eng, av, cv, tv, adam = _engine_for(g, actor, critic, arrays, hp, K=100)     # max_burst is clamped to 64
+        assert eng.max_burst == 64
+        if chunk == K:
+            lq, lp = eng.update(K, idx=idx, eps=eps)
+        else:
+            parts = [eng.update(1, idx=idx[k:k + 1], eps=eps[k:k + 1]) for k in range(K)]
+            lq, lp = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+        torch.cuda.synchronize()
+        assert eng.adam_steps() == (K, K)
+        outs.append((lq.cpu(), lp.cpu(), eng._keep["actor"].cpu(), eng._keep["critic"].cpu(), eng._keep["target"].cpu()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_optimizer_state_loaded_after_first_update_is_adopted():
+    """opt.load_state_dict() AFTER the engine bound the optimizer replaces opt.state's tensors: the binding must notice and
+    adopt the loaded moments / step count instead of silently stepping its old arenas."""
+    import torch.optim as optim
+    from copy import deepcopy
+    from torch_actor_critic_b200.buffer.replay_buffer import ReplayBuffer
+    from torch_actor_critic_b200.networks.linear import Actor, DoubleCritic
+    from torch_actor_critic_b200.sac.algorithm import SAC
+    g, actor_np, critic_np, arrays, hp = load_case("small")
+    O, A, B = int(g["obs_dim"]), int(g["act_dim"]), int(g["batch"])
+    H = [int(h) for h in g["hidden"]]
+
+    def fresh():
+        actor, critic = Actor(O, A, H, act_limit=hp.act_limit), DoubleCritic(O, A, H)
+        actor.load_state_dict({k: torch.tensor(v) for k, v in actor_np.items()})
+        critic.load_state_dict({k: torch.tensor(v) for k, v in critic_np.items()})
+        buf = ReplayBuffer(len(arrays["rewards"]), O, A)
+        buf.store_many(arrays["state"], arrays["actions"], arrays["rewards"], arrays["next_state"], arrays["done"])
+        sac = SAC(alpha=0.2, gamma=0.99, polyak=0.995, reward_scale=1.0, epochs=1, batch_size=B, start_steps=0, steps_per_epoch=1,
+                  max_ep_len=1, update_after=0, update_every=4, save_every=1)
+        return sac, actor, critic, deepcopy(critic), buf, optim.Adam(actor.parameters(), lr=3e-4), optim.Adam(critic.parameters(), lr=3e-4)
+
+    idx, eps = g["idx"], g["eps"]
+    sac, actor, critic, target, buf, pi_opt, q_opt = fresh()
+    sac.update_burst(2, actor, critic, target, buf, pi_opt, q_opt, idx=idx[:2], eps=eps[:2])
+    snap = dict(a=deepcopy(actor.state_dict()), c=deepcopy(critic.state_dict()), t=deepcopy(target.state_dict()),
+                pi=deepcopy(pi_opt.state_dict()), q=deepcopy(q_opt.state_dict()))
+    sac.update_burst(1, actor, critic, target, buf, pi_opt, q_opt, idx=idx[2:3], eps=eps[2:3])
+    want = (actor.arena.clone(), critic.arena.clone())
+    # roll everything back to the snapshot IN PLACE on the already-bound objects, then repeat the third update
+    actor.load_state_dict(snap["a"]); critic.load_state_dict(snap["c"]); target.load_state_dict(snap["t"])
+    pi_opt.load_state_dict(snap["pi"]); q_opt.load_state_dict(snap["q"])
+    sac.update_burst(1, actor, critic, target, buf, pi_opt, q_opt, idx=idx[2:3], eps=eps[2:3])
+    torch.cuda.synchronize()
+    assert torch.equal(actor.arena, want[0]) and torch.equal(critic.arena, want[1])
+    assert float(q_opt.state_dict()["state"][0]["step"]) == 3 == float(pi_opt.state_dict()["state"][0]["step"])

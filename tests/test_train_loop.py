@@ -80,6 +80,15 @@ def test_sac_train_runs_the_reference_flow(tmp_path, monkeypatch):
     tgt = sac.target_critic.state_dict()
     assert all(torch.isfinite(v).all() for v in tgt.values())
     assert any(not torch.equal(tgt[k], v) for k, v in critic.state_dict().items())
+    # checkpoint artifacts with the reference's names (sac/algorithm.py:172-180): whole modules + auxiliaries, loadable
+    ck = tmp_path / "sacb200_checkpoints" / "epoch_0"
+    actor_l = torch.load(ck / "actor.pt", weights_only=False); critic_l = torch.load(ck / "critic.pt", weights_only=False)
+    aux = torch.load(ck / "auxiliaries.pt", weights_only=False)
+    assert type(actor_l).__name__ == "Actor" and type(critic_l).__name__ == "DoubleCritic" and aux["epoch"] == 0
+    assert set(aux) == {"pi_opt", "q_opt", "epoch"} and actor_l.arena.is_cuda
+    assert set(actor_l.state_dict()) == set(actor.state_dict())
+    s0 = torch.as_tensor(env.reset())
+    assert torch.equal(actor_l(s0, deterministic=True)[0], actor_l(s0, deterministic=True)[0])
     # acting path: deterministic action for evaluation (run_agent.py:37) stays inside the action limits
     act, _ = actor(env.reset(), deterministic=True)
     assert act.shape == (3,) and float(act.abs().max()) <= 1.0

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SACB200_LIB") or os.path.join(_HERE, "libsacb200.so")   # override: investigation builds
 
-SACB_OK, SACB_ERR_INVALID, SACB_ERR_CUDA, SACB_ERR_STATE, SACB_ERR_SAMPLE, SACB_ERR_NCCL = 0, -1, -2, -3, -4, -5
+SACB_OK, SACB_ERR_INVALID, SACB_ERR_CUDA, SACB_ERR_STATE, SACB_ERR_SAMPLE, SACB_ERR_NCCL, SACB_ERR_PEER = 0, -1, -2, -3, -4, -5, -6
 FLAG_CANONICAL_LOGPROB, FLAG_PI_FROM_STATES, FLAG_NO_ACTOR_GRAD_SYNC = 1, 2, 4
 
 
@@ -68,6 +68,7 @@ _PROTOS = {
     "sacb_sync_params": (C.c_int, [_P, _U]),
     "sacb_peer_export": (C.c_int, [_P, _P, C.POINTER(_I64)]),
     "sacb_peer_bind": (C.c_int, [_P, _P, _I32, _I32]),
+    "sacb_peer_status": (C.c_int, [_P, _U]),
     "sacb_debug_read": (C.c_int, [_P, C.c_char_p, _P, _I64, C.POINTER(_I64)]),
     "sacb_debug_profile": (C.c_int, [_P, _I32, _P, _I64, C.POINTER(_I32), C.POINTER(_I32), _U]),
     "sacb_launch_count": (_I64, [_P]),

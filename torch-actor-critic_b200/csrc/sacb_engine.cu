@@ -101,6 +101,7 @@ struct sacb_engine {
     float *pa = nullptr, *pc = nullptr, *pt = nullptr;
     float *ma = nullptr, *va = nullptr, *mc = nullptr, *vc = nullptr;
     long long step_pi = 0, step_q = 0;
+    long long exch_pi = 0, exch_q = 0;          // gradient exchanges done so far (peer-flag epochs): never reset by a re-bind
     float *bs = nullptr, *ba = nullptr, *br = nullptr, *bs2 = nullptr;
     uint8_t* bd = nullptr;
     long long cap = 0, ptr = 0, size = 0;
@@ -136,6 +137,9 @@ struct sacb_engine {
     int peer_mode = 0;
     float* peer_ws[kMaxPeers] = {nullptr};
     float* peer_flags = nullptr;
+    unsigned int* abort_host = nullptr;        // host-mapped abort word of the peer exchange (see RunArgs.abort_word)
+    unsigned int* abort_dev = nullptr;
+    unsigned long long peer_timeout_ns = 20000000000ULL;
 };
 
 static void compute_layout(const sacb_config& c, sacb_layout_info& L) {
@@ -163,9 +167,8 @@ static int check_cfg(const sacb_config* c) {
     if (!c) return fail(SACB_ERR_INVALID, "null config");
     if (c->struct_size != sizeof(sacb_config)) return fail(SACB_ERR_INVALID, "sacb_config size mismatch (ABI): got %u want %zu", c->struct_size, sizeof(sacb_config));
     if (c->obs_dim < 1 || c->act_dim < 1 || c->hidden1 < 1 || c->hidden2 < 1) return fail(SACB_ERR_INVALID, "dims must be positive");
-    if (c->batch_size < 1 || c->batch_size > 65536) return fail(SACB_ERR_INVALID, "batch_size out of range");
+    if (c->batch_size < 1 || c->batch_size > 16384) return fail(SACB_ERR_INVALID, "batch_size out of range (1..16384, the on-device sampler's limit)");
     if (c->max_burst < 1 || c->max_burst > kMaxBurst) return fail(SACB_ERR_INVALID, "max_burst must be in [1, %d]", kMaxBurst);
-    if (c->flags & SACB_FLAG_PI_FROM_STATES) return fail(SACB_ERR_INVALID, "SACB_FLAG_PI_FROM_STATES is not implemented");
     return 0;
 }
 
@@ -258,7 +261,8 @@ __global__ void __launch_bounds__(256) draw_indices_kernel(long long* __restrict
     const unsigned long long u = counter0 + blockIdx.x;
     auto draw_below = [&](int i, int round, unsigned long long bound) -> long long {
         curandStatePhilox4_32_10_t st;
-        curand_init(seed, (u << 20) + (unsigned long long)i, (unsigned long long)round, &st);
+        // Philox offsets count single 32-bit outputs and curand4 consumes four: round r starts at output 4r
+        curand_init(seed, (u << 20) + (unsigned long long)i, 4ULL * (unsigned long long)round, &st);
         uint4 r = curand4(&st);
         unsigned long long x = ((unsigned long long)r.x << 32) | r.y;
         return (long long)__umul64hi(x, bound);
@@ -368,7 +372,9 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
     ra.peer_rank = e->rank;
     for (int r = 0; r < kMaxPeers; ++r) ra.peer_ws[r] = e->peer_ws[r];
     ra.peer_off_flags = e->peer_flags - e->ws;
-    ra.epoch_q = e->step_q; ra.epoch_pi = e->step_pi;
+    ra.epoch_q = e->exch_q; ra.epoch_pi = e->exch_pi;
+    ra.abort_word = e->peer_mode ? e->abort_dev : nullptr;
+    ra.peer_timeout_ns = e->peer_timeout_ns;
     ra.grad_div = (float)e->world;
     ra.flags = c.flags;
     ra.O = c.obs_dim; ra.A = c.act_dim; ra.H1 = c.hidden1; ra.H2 = c.hidden2; ra.B = c.batch_size;
@@ -444,6 +450,7 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     CU(cudaFuncSetAttribute(sac_phase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     CU(cudaFuncSetAttribute(sac_phase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesT5));
     CU(cudaFuncSetAttribute(draw_indices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * (int)sizeof(long long)));
+    CU(cudaFuncSetAttribute(actor_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // per device: set at every create
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sac_phase_kernel<false>, kThreads, kSmemBytes));
     if (occ < 1) { delete e; return fail(SACB_ERR_CUDA, "sac_phase_kernel does not fit on an SM"); }
@@ -502,6 +509,7 @@ int sacb_destroy(sacb_handle e) {
     cudaFree(e->ws); cudaFree(e->idx_buf); cudaFree(e->perm_buf); cudaFree(e->eps_buf); cudaFree(e->barrier);
     cudaFree(e->d_jobs); cudaFree(e->d_phases);
     if (e->stage) cudaFreeHost(e->stage);
+    if (e->abort_host) cudaFreeHost(e->abort_host);
     if (e->stage_ev) cudaEventDestroy(e->stage_ev);
     delete e;
     return 0;
@@ -699,6 +707,8 @@ int sacb_update(sacb_handle e, int32_t n_updates, const int64_t* idx_in, const f
     if (int r = need(e->bs != nullptr, "replay buffer")) return r;
     if (n_updates < 0 || n_updates > e->cfg.max_burst) return fail(SACB_ERR_INVALID, "n_updates %d exceeds max_burst %d", n_updates, e->cfg.max_burst);
     if (n_updates == 0) return 0;
+    if (e->abort_host && *(volatile unsigned int*)e->abort_host)
+        return fail(SACB_ERR_PEER, "a previous data-parallel burst timed out waiting for rank %u", *(volatile unsigned int*)e->abort_host - 1);
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(e->cfg.device));
     if (int r = upload_programs(e, st)) return r;
@@ -742,6 +752,7 @@ int sacb_update(sacb_handle e, int32_t n_updates, const int64_t* idx_in, const f
         }
     }
     e->step_pi += n_updates; e->step_q += n_updates;
+    e->exch_pi += n_updates; e->exch_q += n_updates;
     return 0;
 }
 
@@ -785,7 +796,7 @@ int sacb_update_critic(sacb_handle e, const float* eps_in, float* loss_q, uintpt
         if (int r = allreduce(e, e->gc, e->lay.critic_floats, st)) return r;
         if (int r = run_phases(e, ra, e->ph_crit_adam, e->ph_crit_adam + 1, 0, 1, st)) return r;
     }
-    e->step_q += 1;
+    e->step_q += 1; e->exch_q += 1;
     return 0;
 }
 
@@ -813,7 +824,7 @@ int sacb_update_policy(sacb_handle e, const float* eps_in, float* loss_pi, uintp
         if (int r = allreduce(e, e->ga, e->lay.actor_floats, st)) return r;
         if (int r = run_phases(e, ra, adam, e->p_policy.end, 0, 1, st)) return r;
     }
-    e->step_pi += 1;
+    e->step_pi += 1; e->exch_pi += 1;
     return 0;
 }
 
@@ -850,8 +861,6 @@ int sacb_actor_forward(sacb_handle e, const float* x, int32_t n, const float* ep
             a.seed = e->cfg.seed + 0xA24BAED4963EE407ULL * (unsigned long long)(e->rank + 1);
             a.counter = (e->rng_counter++) << 24;
             a.log_min_std = e->cfg.log_min_std; a.log_max_std = e->cfg.log_max_std; a.act_limit = e->cfg.act_limit; a.flags = e->cfg.flags;
-            static bool attr_set = false;
-            if (!attr_set) { CU(cudaFuncSetAttribute(actor_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
             actor_act_kernel<<<kActCluster, 256, smem, st>>>(a);
             CU(cudaGetLastError());
             e->launches++;
@@ -952,8 +961,29 @@ int sacb_peer_bind(sacb_handle e, const uint8_t* handles, int32_t rank, int32_t 
         CU(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
         e->peer_ws[r] = (float*)p;
     }
+    if (!e->abort_host) {
+        CU(cudaHostAlloc((void**)&e->abort_host, sizeof(unsigned int), cudaHostAllocMapped));
+        *e->abort_host = 0;
+        CU(cudaHostGetDevicePointer((void**)&e->abort_dev, e->abort_host, 0));
+    }
+    if (const char* t = getenv("SACB_PEER_TIMEOUT_MS")) {
+        const long long ms = atoll(t);
+        if (ms > 0) e->peer_timeout_ns = (unsigned long long)ms * 1000000ULL;
+    }
     e->rank = rank; e->world = world; e->peer_mode = 1;
     e->dirty = true;
+    return 0;
+}
+
+// 0 = healthy.  Synchronises the stream first, so that a timeout raised by the launch in flight is seen.
+int sacb_peer_status(sacb_handle e, uintptr_t stream) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    if (!e->peer_mode || !e->abort_host) return 0;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    const unsigned ab = *(volatile unsigned int*)e->abort_host;
+    if (ab) return fail(SACB_ERR_PEER, "in-kernel gradient exchange timed out after %.1f s waiting for rank %u (a peer died or stalled); "
+                                       "parameters of this replica are no longer valid", e->peer_timeout_ns * 1e-9, ab - 1);
     return 0;
 }
 
@@ -1056,6 +1086,7 @@ int sacb_debug_profile(sacb_handle e, int32_t n_updates, uint64_t* out, int64_t 
     CU(cudaMemcpy(out, d, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     CU(cudaFree(d));
     e->step_pi += n_updates; e->step_q += n_updates;
+    e->exch_pi += n_updates; e->exch_q += n_updates;
     if (n_phases) *n_phases = np;
     if (n_ctas) *n_ctas = e->grid_coop;
     return 0;

@@ -49,6 +49,11 @@ static void build_programs(sacb_engine* e) {
     const bool fuse_heads = 2 * A <= 16 && e->tf32x3 != 3, fuse_dpi = A <= 16 && e->tf32x3 != 3;
     const int tnH1 = (H1 + e->tile_n - 1) / e->tile_n;
     const bool actor_sync = !(c.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC);
+    // SACB_FLAG_PI_FROM_STATES: the canonical actor loss, pi = actor(states) instead of actor(next_states)
+    // (sac/algorithm.py:37).  The trunk can then no longer be shared between the two noise draws: update_policy evaluates
+    // the actor again on the state columns of xs = [s | a], and the next batch's gather (which overwrites xs) can no longer
+    // overlap the last phase, so it runs as the first phase of every update.
+    const bool pi_states = (c.flags & SACB_FLAG_PI_FROM_STATES) != 0;
     // One GPU, mma.sync / FFMA tiles: nothing sits between backward() and optimizer.step(), so every job that finishes a
     // gradient (dW tiles, bias column sums, the loss reduction's db2) applies Adam (+ Polyak) in its own epilogue and the two
     // Adam phases disappear (18 -> 16 phases).  In-place parameter updates must not race with a dX GEMM that reads the
@@ -63,9 +68,10 @@ static void build_programs(sacb_engine* e) {
         return j; };
 
     // ---- job factories -------------------------------------------------------------------------------------------
-    auto actor_l0 = [&](int dyn, int b_static) {
-        Job j = b.gemm(G_FWD, E_BIAS_RELU, e->s2buf, lds, 0, PA + L.actor_w0, O, 0, e->ah1, H1, 0, B, H1, O, 1, dyn);
-        j.bias = PA + L.actor_b0; j.b_static = b_static; if (fuse_adam && !dyn) j.stg = 1; return j; };
+    auto actor_l0 = [&](int dyn, int b_static, bool from_states = false) {
+        Job j = from_states ? b.gemm(G_FWD, E_BIAS_RELU, e->xs, ldx, 0, PA + L.actor_w0, O, 0, e->ah1, H1, 0, B, H1, O, 1, dyn)
+                            : b.gemm(G_FWD, E_BIAS_RELU, e->s2buf, lds, 0, PA + L.actor_w0, O, 0, e->ah1, H1, 0, B, H1, O, 1, dyn);
+        j.bias = PA + L.actor_b0; j.b_static = b_static; if (fuse_adam && !dyn && !from_states) j.stg = 1; return j; };
     auto actor_l1 = [&](int dyn) {
         Job j = b.gemm(G_FWD, E_BIAS_RELU, e->ah1, H1, 0, PA + L.actor_w1, H1, 0, e->ah2, H2, 0, B, H2, H1, 1, dyn);
         j.bias = PA + L.actor_b1; j.b_static = 1;
@@ -76,9 +82,9 @@ static void build_programs(sacb_engine* e) {
     auto actor_heads = [&](int dyn) {
         Job j = b.gemm(G_FWD, E_BIAS, e->ah2, H2, 0, PA + L.actor_w_mu, H2, 0, e->heads, ldh, 0, B, 2 * A, H2, 1, dyn);
         j.bias = PA + L.actor_b_mu; j.b_static = 1; return j; };
-    auto row_heads = [&](int dyn) {
+    auto row_heads = [&](int dyn, int passes = 0) {
         Job j = Builder::zero();
-        j.type = J_ROW_HEADS; j.A = e->heads; j.C = e->heads; j.lda = ldh; j.M = B; j.rows_dynamic = dyn;
+        j.type = J_ROW_HEADS; j.i3 = passes;        // passes: 0 = whatever RunArgs.pass_mask says, else ANDed with it j.A = e->heads; j.C = e->heads; j.lda = ldh; j.M = B; j.rows_dynamic = dyn;
         j.out0 = e->x2; j.out1 = e->logp; j.out2 = e->xp; j.out3 = e->logp + B; j.ldc = ldx; j.i0 = O;
         if (fuse_heads) { j.i1 = e->tnH2; j.B = e->hpart; j.i2 = B; j.bias = PA + L.actor_b_mu; }
         j.ntiles = (B + kRowsHeads - 1) / kRowsHeads; return j; };
@@ -141,21 +147,21 @@ static void build_programs(sacb_engine* e) {
         q2_late_rows = late_blocks * e->tile_m;
         if (2 * t_l1 + late_blocks * e->tnH2 > cap || q2_late_rows >= B) { spread = false; q2_late_rows = 0; }
     }
-    auto actor_forward = [&](int dyn, bool with_critic, int l0_static) {
+    auto actor_forward = [&](int dyn, bool with_critic, int l0_static, int passes = 0, bool from_states = false) {
         if (with_critic && spread) {
             b.phase(); b.add(actor_l0(dyn, l0_static)); b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 0));
             b.phase(); b.add(actor_l1(dyn)); b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 1));
-            b.phase(); b.add(row_heads(dyn)); b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 1));
+            b.phase(); b.add(row_heads(dyn, passes)); b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 1));
             b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1, 0, B - q2_late_rows));
             return;
         }
         // tile budget: one round = one tile per SM.  A.L0 + C.L0[q1] (e.g. 64 + 64 tiles) now, C.L0[q2] rides as the
         // cheap second tile of the next phase (its consumer C.L1[q2] runs one phase later anyway)
-        b.phase(); b.add(actor_l0(dyn, l0_static)); if (with_critic) b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 0));
+        b.phase(); b.add(actor_l0(dyn, l0_static, from_states)); if (with_critic) b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 0));
         b.phase(); b.add(actor_l1(dyn));
         if (with_critic) { b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 1)); b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 1)); }
         if (!fuse_heads) { b.phase(); b.add(actor_heads(dyn)); if (with_critic) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1)); }
-        b.phase(); b.add(row_heads(dyn));
+        b.phase(); b.add(row_heads(dyn, passes));
         if (with_critic && fuse_heads) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1));
     };
 
@@ -204,8 +210,9 @@ static void build_programs(sacb_engine* e) {
             j.mask = e->ah1; j.ldmask = H1; j.b_static = 1;
             b.add(j); };
         auto dW0 = [&]() {
-            Job j = with_adam(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->s2buf, lds, 0, GA + L.actor_w0, O, 0, H1, O, B, 1), false);
-            if (fuse_adam) j.stg = 2;          // the next batch's s' is being gathered into the other buffer during this phase
+            Job j = pi_states ? with_adam(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->xs, ldx, 0, GA + L.actor_w0, O, 0, H1, O, B, 1), false)
+                              : with_adam(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->s2buf, lds, 0, GA + L.actor_w0, O, 0, H1, O, B, 1), false);
+            if (fuse_adam && !pi_states) j.stg = 2;   // the next batch's s' is being gathered into the other buffer during this phase
             j.b_static = 1;
             b.add(j);
             b.add(with_adam(b.colsum(e->adh1, H1, 0, nullptr, 0, GA + L.actor_b0, 0, B, H1, 1), false)); };
@@ -234,11 +241,11 @@ static void build_programs(sacb_engine* e) {
         // every later batch is prefetched by the last phase of the previous update (the indices of the whole burst
         // are known up front), so the HBM latency of the random-row gather is off the critical path.
         int p0 = b.phase();
-        e->phases[p0].pad = 1;
+        e->phases[p0].pad = pi_states ? 0 : 1;
         b.add(gather(0));
     }
     e->ph_crit_begin = (int)e->phases.size();
-    actor_forward(0, true, /*actor W0 was just written by Adam(actor) of the previous update*/ 0);
+    actor_forward(0, true, /*actor W0 was just written by Adam(actor) of the previous update*/ 0, pi_states ? 1 : 0);
     b.phase(); b.add(critic_l0(PT, e->x2, e->th1, 0, 1));                                   // target critic on (s', a2)
     b.phase(); b.add(critic_l1(PT, e->th1, e->th2, e->qtpart, 0, 0, 2));
     if (spread && q2_late_rows > 0) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1, B - q2_late_rows, q2_late_rows));
@@ -281,13 +288,14 @@ static void build_programs(sacb_engine* e) {
         b.phase(); if (e->peer_mode) b.add(peer_signal(true)); b.add(adam(true));            // Adam(critic) [+ Polyak]
     }
     e->ph_pi_begin = (int)e->phases.size();
+    if (pi_states) actor_forward(0, false, 1, 2, true);    // pi = actor(states): second trunk evaluation, actor-loss pass only
     e->ph_pi_adam = policy_tail(false);
-    b.add(gather(1));                                      // prefetch the next update's batch (staging tiles are idle here)
+    if (!pi_states) b.add(gather(1));                      // prefetch the next update's batch (staging tiles are idle here)
     e->p_update.end = (int)e->phases.size();
 
     // ---------------- standalone update_policy (actor trunk recomputed) ----------------
     e->p_policy.begin = (int)e->phases.size();
-    actor_forward(0, false, 0);
+    actor_forward(0, false, 0, 0, pi_states);
     policy_tail(true);
     e->p_policy.end = (int)e->phases.size();
 

@@ -16,6 +16,9 @@ ACTOR_PARAM_NAMES = ("layers.0.weight", "layers.0.bias", "layers.1.weight", "lay
 CRITIC_PARAM_NAMES = tuple(f"{q}.layers.{i}.{wb}" for q in ("q1", "q2") for i in (0, 1, 2) for wb in ("weight", "bias"))
 
 
+MAX_BURST = 64          # updates per launch (kMaxBurst in csrc/sacb_device.cuh); Engine.update splits longer bursts
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -106,7 +109,8 @@ class Engine:
         device = torch.device(device).index if not isinstance(device, int) else device
         self.device = int(device)
         self.obs_dim, self.act_dim, self.hidden_sizes = int(obs_dim), int(act_dim), [int(h) for h in hidden_sizes]
-        self.batch_size, self.max_burst = int(batch_size), int(max_burst)
+        self.batch_size, self.max_burst = int(batch_size), max(1, min(int(max_burst), MAX_BURST))
+        max_burst = self.max_burst
         self.cfg = make_config(obs_dim, act_dim, hidden_sizes, batch_size, max_burst, self.device, **scalars)
         self.layout = SacbLayout()
         check(lib.sacb_layout(C.byref(self.cfg), C.byref(self.layout)))
@@ -224,7 +228,12 @@ class Engine:
             if tuple(eps.shape) != (n, 2, self.batch_size, self.act_dim):
                 raise ValueError(f"eps must be [{n},2,{self.batch_size},{self.act_dim}]")
         lq = torch.empty(n, device=d); lp = torch.empty(n, device=d)
-        check(self._lib.sacb_update(self._h, n, _ptr(idx), _ptr(eps), _ptr(lq), _ptr(lp), self._stream()))
+        # one launch per <= max_burst updates (the kernel carries a 64-entry table of Adam step scalars); a longer burst
+        # (e.g. update_every = 100) is a sequence of launches -- the Adam step counters carry across calls
+        for k0 in range(0, n, self.max_burst):
+            m = min(self.max_burst, n - k0)
+            check(self._lib.sacb_update(self._h, m, _ptr(idx[k0:k0 + m]) if idx is not None else 0,
+                                        _ptr(eps[k0:k0 + m]) if eps is not None else 0, _ptr(lq[k0:]), _ptr(lp[k0:]), self._stream()))
         return lq, lp
 
     def load_batch(self, states, actions, rewards, next_states, done):
@@ -323,6 +332,10 @@ class Engine:
 
     def sync_params(self):
         check(self._lib.sacb_sync_params(self._h, self._stream()))
+
+    def peer_status(self):
+        """Raises SacbError(SACB_ERR_PEER) when the in-kernel gradient exchange timed out on a dead / stalled rank."""
+        check(self._lib.sacb_peer_status(self._h, self._stream()))
 
     # ------------------------------------------------------------------ debug
     def debug_read(self, name):

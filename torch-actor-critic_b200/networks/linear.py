@@ -25,7 +25,26 @@ def _device_index(device):
     return torch.device(device).index if not isinstance(device, int) else device
 
 
-class Actor(nn.Module):
+def _rebuild(cls, kwargs, state, requires_grad):
+    """Unpickling hook (mlflow.pytorch.load_model / torch.load of a whole module, main.py:33-34, run_agent.py): re-create the
+    arena-backed module on the current CUDA device and load the saved parameters.  Engines are re-created lazily."""
+    m = cls(**kwargs)
+    m.load_state_dict(state)
+    for p, rg in zip(m.parameters(), requires_grad):
+        p.requires_grad = rg
+    return m
+
+
+class _Picklable:
+    def _ctor_kwargs(self):
+        raise NotImplementedError
+
+    def __reduce__(self):
+        state = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        return (_rebuild, (type(self), self._ctor_kwargs(), state, [p.requires_grad for p in self.parameters()]))
+
+
+class Actor(_Picklable, nn.Module):
     """tanh-Gaussian policy, reference networks/linear.py:13-53.
 
     forward(x, deterministic=False, with_logprob=True) -> (pi_action, logprob | None); x may be [B,O] or [O]."""
@@ -46,6 +65,10 @@ class Actor(nn.Module):
         self.mu_layer = ArenaLinear(h2, act_dim, v["mu_layer.weight"], v["mu_layer.bias"])
         self.log_std_layer = ArenaLinear(h2, act_dim, v["log_std_layer.weight"], v["log_std_layer.bias"])
         self._engine = None
+
+    def _ctor_kwargs(self):
+        return dict(obs_dim=self.obs_dim, act_dim=self.act_dim, hidden_sizes=self.hidden_sizes, log_min_std=self.log_min_std,
+                    log_max_std=self.log_max_std, act_limit=self.act_limit)
 
     def _fwd_engine(self) -> Engine:
         if self._engine is None:
@@ -118,7 +141,7 @@ class Critic(nn.Module):
         return qs[self._slot].reshape(*lead)
 
 
-class DoubleCritic(nn.Module):
+class DoubleCritic(_Picklable, nn.Module):
     """Twin Q networks, reference networks/linear.py:72-79.  forward(state, action) -> (q1, q2)."""
 
     def __init__(self, obs_dim: int, act_dim: int, hidden_sizes: t.List[int], device=None):
@@ -131,6 +154,9 @@ class DoubleCritic(nn.Module):
         self.q1 = Critic(obs_dim, act_dim, hidden_sizes, device=self._dev, _arena=self.arena, _slot=0, _layout=self._layout)
         self.q2 = Critic(obs_dim, act_dim, hidden_sizes, device=self._dev, _arena=self.arena, _slot=1, _layout=self._layout)
         self._engine = None
+
+    def _ctor_kwargs(self):
+        return dict(obs_dim=self.obs_dim, act_dim=self.act_dim, hidden_sizes=self.hidden_sizes)
 
     def _fwd_engine(self) -> Engine:
         if self._engine is None:

@@ -105,6 +105,14 @@ class _AdamBinding:
                 self.steps = int(float(st["step"]))
             opt.state[p] = {"step": self.step_tensor, "exp_avg": mv[n], "exp_avg_sq": vv[n]}
         self.step_tensor.fill_(float(self.steps))
+        self._probe = (params[names[0]], mv[names[0]].data_ptr())
+
+    def still_bound(self) -> bool:
+        """False once `opt.load_state_dict()` (or anything else) replaced the moment tensors the engine steps: the
+        binding must then be rebuilt so that the loaded state is adopted instead of silently ignored."""
+        p, ptr = self._probe
+        st = self.opt.state.get(p)
+        return bool(st) and st.get("exp_avg") is not None and st["exp_avg"].data_ptr() == ptr and st.get("step") is self.step_tensor
 
     def advance(self, n):
         self.steps += n
@@ -128,6 +136,7 @@ class SAC(object):
         self.update_every = update_every
         self.save_every = save_every
         self._engines = {}
+        self._bindings = {}          # id(optimizer) -> _AdamBinding, shared by every engine that steps that optimizer
         self.seed = 0
         setup_pytorch_for_mpi()
 
@@ -138,7 +147,7 @@ class SAC(object):
         key = (id(actor), id(critic), int(batch))
         ent = self._engines.get(key)
         if ent is None:
-            eng = Engine(actor.obs_dim, actor.act_dim, actor.hidden_sizes, batch_size=batch, max_burst=max(int(self.update_every), 1),
+            eng = Engine(actor.obs_dim, actor.act_dim, actor.hidden_sizes, batch_size=batch, max_burst=max(int(self.update_every), 1),   # clamped to 64 per launch; longer bursts are split (Engine.update)
                          device=actor._dev, alpha=self.alpha, gamma=self.gamma, polyak=self.polyak,
                          reward_scale=self.reward_scale, log_min_std=actor.log_min_std, log_max_std=actor.log_max_std,
                          act_limit=actor.act_limit, seed=self.seed, rank=proc_id(), world=num_procs())
@@ -157,12 +166,18 @@ class SAC(object):
             eng.bind_params(actor=actor.arena, critic=critic.arena, target=target.arena)
             ent["target"] = target
         rebind = False
-        if pi_opt is not None and (ent["pi"] is None or ent["pi"].opt is not pi_opt):
-            ent["pi"] = self._bind_opt(pi_opt, actor, True, eng)
-            rebind = True
-        if q_opt is not None and (ent["q"] is None or ent["q"].opt is not q_opt):
-            ent["q"] = self._bind_opt(q_opt, critic, False, eng)
-            rebind = True
+        if pi_opt is not None:
+            b = self._binding(pi_opt, actor, True, eng)
+            if ent["pi"] is not b:
+                ent["pi"], rebind = b, True
+        if q_opt is not None:
+            b = self._binding(q_opt, critic, False, eng)
+            if ent["q"] is not b:
+                ent["q"], rebind = b, True
+        if not rebind and (ent["pi"] is not None or ent["q"] is not None):
+            # the same optimizer may have been stepped through another engine (another batch size): adopt its step count
+            sa, sc = eng.adam_steps()
+            rebind = (ent["pi"] is not None and ent["pi"].steps != sa) or (ent["q"] is not None and ent["q"].steps != sc)
         if rebind:
             pi, q = ent["pi"], ent["q"]
             eng.bind_adam(pi.m if pi else None, pi.v if pi else None, pi.steps if pi else 0,
@@ -173,6 +188,15 @@ class SAC(object):
                 eng.set_scalar(f"lr_{which}", lr)
                 eng.set_scalar("beta1", b1); eng.set_scalar("beta2", b2); eng.set_scalar("adam_eps", eps)
         return eng
+
+    def _binding(self, opt, module, is_actor, eng: Engine):
+        """One _AdamBinding per optimizer (shared across engines); rebuilt when the optimizer's state tensors were replaced
+        (`load_state_dict` after the first update), so the loaded moments / step are adopted."""
+        b = self._bindings.get(id(opt))
+        if b is None or b.opt is not opt or not b.still_bound():
+            b = self._bind_opt(opt, module, is_actor, eng)
+            self._bindings[id(opt)] = b
+        return b
 
     @staticmethod
     def _bind_opt(opt, module, is_actor, eng: Engine):
@@ -236,13 +260,19 @@ class SAC(object):
         aux = {"pi_opt": pi_opt.state_dict(), "q_opt": q_opt.state_dict(), "epoch": epoch}
         try:
             import mlflow
-            mlflow.pytorch.log_state_dict({"actor": actor.state_dict(), "critic": critic.state_dict()}, artifact_path="models")
+            # the reference's artifact layout (sac/algorithm.py:172-180): main.py:load_session and run_agent.py read
+            # artifacts/actor and artifacts/critic back with mlflow.pytorch.load_model, artifacts/auxiliaries with
+            # load_state_dict.  The modules pickle as plain state (arena + dims) and re-create their engine on load.
+            mlflow.pytorch.log_model(actor, "actor")
+            mlflow.pytorch.log_model(critic, "critic")
             mlflow.pytorch.log_state_dict(aux, artifact_path="auxiliaries")
         except ImportError:
             import os
-            os.makedirs("sacb200_checkpoints", exist_ok=True)
-            torch.save({"actor": actor.state_dict(), "critic": critic.state_dict(), **aux},
-                       os.path.join("sacb200_checkpoints", f"epoch_{epoch}.pt"))
+            d = os.path.join("sacb200_checkpoints", f"epoch_{epoch}")
+            os.makedirs(d, exist_ok=True)
+            torch.save(actor, os.path.join(d, "actor.pt"))            # same three artifacts, torch.save instead of mlflow
+            torch.save(critic, os.path.join(d, "critic.pt"))
+            torch.save(aux, os.path.join(d, "auxiliaries.pt"))
 
     def train(self, start_epoch: int, env, actor: nn.Module, critic: nn.Module, buffer: ReplayBuffer,
               pi_opt: optim.Optimizer, q_opt: optim.Optimizer, render: bool = True, logging: bool = True):

@@ -1,9 +1,11 @@
 """Data-parallel helpers with the names of the reference's sac/mpi.py, on torch.distributed instead of mpi4py:
 one process per GPU, NCCL over NVLink for device tensors (gloo for CPU tensors in tests).
 
-Inside a training burst the gradient averaging does not go through this module at all: the engine all-reduces its
-flat gradient arenas with NCCL between the backward and Adam phases (`Engine.comm_init_from_torch`).  These
-functions serve the host-side callers (parameter broadcast at start, scalar statistics) and keep the reference API.
+Inside a training burst the gradient averaging does not go through this module at all: by default the engine sums the
+ranks' flat gradient arenas INSIDE the persistent update kernel (CUDA-IPC peer loads over NVLink in fixed rank order,
+`Engine.peer_init_from_torch`); `SACB_COMM=nccl` selects ncclAllReduce between the backward and Adam launches instead
+(`Engine.comm_init_from_torch`).  These functions serve the host-side callers (parameter broadcast at start, scalar
+statistics) and keep the reference API.
 """
 from __future__ import annotations
 
