@@ -54,11 +54,14 @@ def _check(g, prefix, name, value, rtol, atol):
 
 
 @pytest.mark.parametrize("name", ["small", "ragged", "c1"])
-@pytest.mark.parametrize("mode,tf32x3", [(0, 1), (1, 1), (0, 0), (0, 2), (1, 2)])
-def test_update_matches_reference_golden(name, mode, tf32x3):
+@pytest.mark.parametrize("mode,tf32x3,fold", [(0, 1, 1), (1, 1, 1), (0, 0, 1), (0, 2, 1), (1, 2, 1), (0, 1, 0), (1, 1, 0), (0, 0, 0)])
+def test_update_matches_reference_golden(name, mode, tf32x3, fold, monkeypatch):
     """mode 0 = persistent kernel, 1 = one launch per phase; tf32x3: 0 = plain fp32 FFMA, 1 = mma.sync tensor-core
-    GEMMs with 3xTF32 error compensation, 2 = tcgen05 (TMEM accumulators) with 3xTF32.  Same tolerances for all."""
+    GEMMs with 3xTF32 error compensation, 2 = tcgen05 (TMEM accumulators) with 3xTF32; fold 1 = the folded 8-phase program
+    (row jobs and input layers generated inside the consumer GEMM tiles; applies to tf32x3 0/1), 0 = the first 16-phase
+    program.  Same tolerances for all."""
     from torch_actor_critic_b200.engine import actor_views, critic_views
+    monkeypatch.setenv("SACB_FOLD", str(fold))
     g, actor, critic, arrays, hp = load_case(name)
     eng, av, cv, tv, adam = _engine_for(g, actor, critic, arrays, hp)
     eng.set_mode(mode)
@@ -415,8 +418,9 @@ def test_errors_are_loud():
     assert ei.value.code == _lib.SACB_ERR_STATE
     with pytest.raises(NotImplementedError):
         Engine(3, 2, [8, 8, 8])
-    with pytest.raises(_lib.SacbError):
-        Engine(3, 2, [8, 8], flags=_lib.FLAG_PI_FROM_STATES)
+    with pytest.raises(_lib.SacbError) as ei:
+        Engine(3, 2, [8, 8], batch_size=20000)                       # beyond the on-device sampler's 16384 rows
+    assert ei.value.code == _lib.SACB_ERR_INVALID
 
 
 @pytest.mark.parametrize("tf32x3", [1, 0, 2])

@@ -111,6 +111,11 @@ struct sacb_engine {
     int ldx = 0, lds = 0, ldh = 0, lddpi = 0, tnH2 = 0, row_tiles = 0;
     float *xs, *xp, *x2, *s2buf, *rd, *ah1, *ah2, *heads, *logp, *ch1, *ch2, *th1, *th2, *qpart, *qtpart, *qbuf, *qfw,
         *dh2, *dh1, *dpi, *ghead, *hpart, *dpart, *adh2, *adh1, *lparts_q, *lparts_pi, *loss_scalar, *ga, *gc;
+    // folded program only: critic activations of the actor-loss pass, its Q-dot partials, per-row-block column-sum partials
+    float *cp1, *cp2, *qppart, *colp_b0, *colp_b1, *colp_w2, *colp_ab0, *colp_ab1, *colp_bh;
+    int row_blocks = 0;
+    bool fold_ok = false;           // the folded program exists for this configuration / arithmetic path
+    int last_parity = 0;            // staging parity of the last update executed (debug reads of the folded program)
     long long* idx_buf = nullptr;
     int* perm_buf = nullptr;
     size_t perm_cap = 0;
@@ -124,7 +129,7 @@ struct sacb_engine {
     Job* d_jobs = nullptr;
     Phase* d_phases = nullptr;
     size_t d_jobs_cap = 0, d_phases_cap = 0;
-    ProgRange p_update, p_policy, p_targets, p_actor_fwd, p_critic_fwd[2];
+    ProgRange p_update, p_policy, p_targets, p_actor_fwd, p_critic_fwd[2], p_fold;
     int ph_crit_begin = 0, ph_crit_adam = 0, ph_pi_begin = 0, ph_pi_adam = 0;   // split points inside p_update
     // store staging
     uint8_t* stage = nullptr;
@@ -380,6 +385,24 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
     ra.O = c.obs_dim; ra.A = c.act_dim; ra.H1 = c.hidden1; ra.H2 = c.hidden2; ra.B = c.batch_size;
     ra.s2_stride = (long long)c.batch_size * e->lds;
     ra.pass_mask = 3;
+    {   // the folded program's generators (sacb_fold.cuh)
+        const sacb_layout_info& L = e->lay;
+        FoldPtrs& f = ra.f;
+        const long long B = c.batch_size;
+        if (e->pa) { f.a_w0 = e->pa + L.actor_w0; f.a_b0 = e->pa + L.actor_b0; f.a_wh = e->pa + L.actor_w_mu; f.a_bh = e->pa + L.actor_b_mu; }
+        if (e->pc) { f.c_w0 = e->pc + L.critic_w0[0]; f.c_b0 = e->pc + L.critic_b0[0]; f.c_w2 = e->pc + L.critic_w2[0]; f.c_b2 = e->pc + L.critic_b2[0]; }
+        if (e->pt) { f.t_w0 = e->pt + L.critic_w0[0]; f.t_b0 = e->pt + L.critic_b0[0]; f.t_b2 = e->pt + L.critic_b2[0]; }
+        f.xs = e->xs; f.s2 = e->s2buf; f.rd = e->rd;
+        f.xs_stride = B * e->ldx; f.s2_stride = B * e->lds; f.rd_stride = 2 * B;
+        f.ldx = e->ldx; f.lds = e->lds; f.ldh = e->ldh; f.tnH2 = e->tnH2; f.tnH1x2 = 2 * ((c.hidden1 + e->tile_n - 1) / e->tile_n);
+        f.ah1 = e->ah1; f.ch1 = e->ch1; f.cp1 = e->cp1;
+        f.hpart = e->hpart; f.heads = e->heads; f.logp = e->logp;
+        f.dbg_a2 = e->x2 + c.obs_dim; f.dbg_pi = e->xp + c.obs_dim;
+        f.qpart = e->qpart; f.qtpart = e->qtpart; f.qppart = e->qppart;
+        f.qbuf = e->qbuf; f.lparts_q = e->lparts_q; f.lparts_pi = e->lparts_pi;
+        f.dh2 = e->dh2; f.colp_b1 = e->colp_b1; f.colp_w2 = e->colp_w2;
+        f.dpart = e->dpart; f.ghead = e->ghead; f.adh2 = e->adh2; f.colp_ab1 = e->colp_ab1; f.colp_bh = e->colp_bh;
+    }
 }
 
 // Run phases [pb, pe) for updates [kb, ke).  Cooperative persistent launch unless mode==1 or a single phase.
@@ -474,7 +497,13 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     struct Slot { float** p; size_t o; };
     std::vector<Slot> slots;
     auto want = [&](float*& p, long long n) { slots.push_back({&p, take(n)}); };
-    want(e->xs, B * e->ldx); want(e->xp, B * e->ldx); want(e->x2, B * e->ldx); want(e->s2buf, 2 * B * e->lds); want(e->rd, 2 * B);
+    // staging tiles: two parity buffers each (the folded program gathers the next batch while this one is still in use)
+    want(e->xs, 2 * B * e->ldx); want(e->xp, B * e->ldx); want(e->x2, B * e->ldx); want(e->s2buf, 2 * B * e->lds); want(e->rd, 4 * B);
+    e->row_blocks = (int)((B + kBM - 1) / kBM);
+    const long long RB = e->row_blocks;
+    want(e->cp1, B * 2 * H1); want(e->cp2, B * 2 * H2); want(e->qppart, 2LL * tn16_H2 * B);
+    want(e->colp_b0, RB * 2 * H1); want(e->colp_b1, RB * 2 * H2); want(e->colp_w2, RB * 2 * H2);
+    want(e->colp_ab0, RB * H1); want(e->colp_ab1, RB * H2); want(e->colp_bh, RB * 16);
     want(e->ah1, B * H1); want(e->ah2, B * H2); want(e->heads, B * e->ldh); want(e->logp, 2 * B);
     want(e->ch1, B * 2 * H1); want(e->ch2, B * 2 * H2); want(e->th1, B * 2 * H1); want(e->th2, B * 2 * H2);
     want(e->qpart, 2LL * tn16_H2 * B); want(e->qtpart, 2LL * tn16_H2 * B); want(e->qbuf, 9 * B); want(e->qfw, 2 * B);
@@ -732,8 +761,11 @@ int sacb_update(sacb_handle e, int32_t n_updates, const int64_t* idx_in, const f
     ra.fuse_polyak = 1; ra.pass_mask = 3; ra.k_total = n_updates;
     if (e->world <= 1 || e->peer_mode) {
         // single GPU, or peer mode: the gradient exchange is fused into the Adam phases (NVLink loads from the peers'
-        // arenas), so a data-parallel burst is still ONE persistent launch
-        if (int r = run_phases(e, ra, e->p_update.begin, e->p_update.end, 0, n_updates, st)) return r;
+        // arenas), so a data-parallel burst is still ONE persistent launch -- of the folded 8-phase program when the
+        // configuration allows it (build_fold_program), else of the first 16-phase program
+        const ProgRange& pr = e->fold_ok ? e->p_fold : e->p_update;
+        if (int r = run_phases(e, ra, pr.begin, pr.end, 0, n_updates, st)) return r;
+        e->last_parity = e->fold_ok ? ((n_updates - 1) & 1) : 0;
     } else {
         const bool sync_actor = !(e->cfg.flags & SACB_FLAG_NO_ACTOR_GRAD_SYNC);
         for (int k = 0; k < n_updates; ++k) {
@@ -766,6 +798,7 @@ int sacb_load_batch(sacb_handle e, const float* s, const float* a, const float* 
                                                    e->rd, e->ldx, e->lds);
     CU(cudaGetLastError());
     e->launches++;
+    e->last_parity = 0;
     return 0;
 }
 
@@ -1021,8 +1054,8 @@ int sacb_debug_read(sacb_handle e, const char* name, float* dst, int64_t max_flo
     else if (n == "grad_actor") { src = e->ga; cnt = e->lay.actor_floats; }
     else if (n == "grad_critic") { src = e->gc; cnt = e->lay.critic_floats; }
     else if (n == "loss") { src = e->loss_scalar; cnt = 2; }
-    else if (n == "rewards") { src = e->rd; cnt = B; }
-    else if (n == "done") { src = e->rd + B; cnt = B; }
+    else if (n == "rewards") { src = e->rd + (size_t)e->last_parity * 2 * B; cnt = B; }
+    else if (n == "done") { src = e->rd + (size_t)e->last_parity * 2 * B + B; cnt = B; }
     else return fail(SACB_ERR_INVALID, "unknown debug array '%s'", name);
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaDeviceSynchronize());
@@ -1044,11 +1077,12 @@ int sacb_debug_profile(sacb_handle e, int32_t n_updates, uint64_t* out, int64_t 
     if (int r = check_train_bound(e, 3)) return r;
     if (int r = need(e->bs != nullptr, "replay buffer")) return r;
     if (n_updates < 1 || n_updates > e->cfg.max_burst) return fail(SACB_ERR_INVALID, "bad n_updates");
-    if (e->world > 1) return fail(SACB_ERR_INVALID, "profile is single-GPU only");
+    if (e->world > 1 && !e->peer_mode) return fail(SACB_ERR_INVALID, "profile needs a single launch per burst: one GPU or peer mode");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(e->cfg.device));
     if (int r = upload_programs(e, st)) return r;
-    const int np = e->p_update.end - e->p_update.begin;
+    const ProgRange& pr = e->fold_ok ? e->p_fold : e->p_update;
+    const int np = pr.end - pr.begin;
     const long long words = (long long)n_updates * np * e->grid_coop * 2;
     if (words > max_words) return fail(SACB_ERR_INVALID, "stamp buffer too small: need %lld words", words);
     unsigned long long* d = nullptr;
@@ -1068,8 +1102,9 @@ int sacb_debug_profile(sacb_handle e, int32_t n_updates, uint64_t* out, int64_t 
     ra.fuse_polyak = 1; ra.pass_mask = 3; ra.prof = d; ra.k_total = n_updates;
     const int saved_mode = e->mode;
     e->mode = 0;
-    int rc = run_phases(e, ra, e->p_update.begin, e->p_update.end, 0, n_updates, st);
+    int rc = run_phases(e, ra, pr.begin, pr.end, 0, n_updates, st);
     e->mode = saved_mode;
+    e->last_parity = e->fold_ok ? ((n_updates - 1) & 1) : 0;
     if (rc) { cudaFree(d); return rc; }
     CU(cudaStreamSynchronize(st));
 #ifdef SACB_TRACE

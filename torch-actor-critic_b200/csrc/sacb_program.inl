@@ -84,7 +84,8 @@ static void build_programs(sacb_engine* e) {
         j.bias = PA + L.actor_b_mu; j.b_static = 1; return j; };
     auto row_heads = [&](int dyn, int passes = 0) {
         Job j = Builder::zero();
-        j.type = J_ROW_HEADS; j.i3 = passes;        // passes: 0 = whatever RunArgs.pass_mask says, else ANDed with it j.A = e->heads; j.C = e->heads; j.lda = ldh; j.M = B; j.rows_dynamic = dyn;
+        j.type = J_ROW_HEADS; j.A = e->heads; j.C = e->heads; j.lda = ldh; j.M = B; j.rows_dynamic = dyn;
+        j.i3 = passes;                              // 0 = whatever RunArgs.pass_mask says, else ANDed with it
         j.out0 = e->x2; j.out1 = e->logp; j.out2 = e->xp; j.out3 = e->logp + B; j.ldc = ldx; j.i0 = O;
         if (fuse_heads) { j.i1 = e->tnH2; j.B = e->hpart; j.i2 = B; j.bias = PA + L.actor_b_mu; }
         j.ntiles = (B + kRowsHeads - 1) / kRowsHeads; return j; };
@@ -327,5 +328,149 @@ static void build_programs(sacb_engine* e) {
             b.add(j);
         }
         e->p_critic_fwd[w].end = (int)e->phases.size();
+    }
+
+    // ---------------- the FOLDED update program (sacb_fold.cuh): 8 phases per update, 10 with a gradient exchange ----------
+    //
+    //   F0*  gather(k)                                  F0'* C.L1 twin on [s|a] (layer 0 generated)      (* first update of a launch)
+    //   F1   A.L1 (layer 0 on s' generated; + heads as post-product)
+    //   F2   T.L1 twin (a2 / logp rows + layer 0 on [s'|a2] generated; + Q-dot)
+    //   F3   C.dh1 twin (backup / dq / dh2 rows generated; column sums for db0, db1, dW2 as per-row-block partials)
+    //   F4   loss_q, db2 || bias / W2 gradients from the partials || C.dW1 twin || C.dW0          [+ Adam fused, Polyak]
+    //   F4a  [exchange] Adam(critic) + Polyak                                                      (world > 1 only)
+    //   F5   Cpi.L1 twin (pi / logp rows + layer 0 on [s|pi] generated; + Q-dot)  ||  gather(k+1)
+    //   F6   Cpi.dh1 twin (min-Q rows generated; + d pi as post-product)
+    //   F7   A.dh1 (head-gradient rows + dh2 generated)  ||  loss_pi  ||  C.L1 twin of update k+1, first row blocks
+    //   F8   A.dWh || A.dW1 || A.dW0 || bias gradients from the partials  [+ Adam fused]  ||  C.L1 of update k+1, remaining rows
+    //   F8a  [exchange] Adam(actor)                                                                (world > 1 only)
+    //
+    // The online critic's forward on (s, a) does not depend on the actor step, so for update k+1 it runs on the CTAs that the
+    // actor's backward GEMMs of update k leave idle (the batch is gathered during F5; every staging tile is parity
+    // double-buffered).  Conditions: mma.sync / FFMA tiles, two noise draws sharing the trunk (no PI_FROM_STATES), heads and
+    // d pi narrow enough for the post-products, and every reduction resident in the 4 stage buffers (H1, H2 <= 256).
+    e->fold_ok = false;
+    {
+        const char* fe = getenv("SACB_FOLD");
+        const bool want_fold = !(fe && atoi(fe) == 0);
+        if (want_fold && e->tf32x3 < 2 && !pi_states && fuse_heads && fuse_dpi && A <= 8 && H1 <= kStages * kBK && H2 <= kStages * kBK &&
+            H1 <= kThreads && H2 <= kThreads && OA <= kGenMaxK0 && kThreads == 256 && e->tnH2 <= 8 && 2 * tnH1 <= 16) {
+            const int RB = e->row_blocks;
+            auto gen_job = [&](Job j, int gen, int gsrc, int gwrite, int row0 = 0) {
+                j.gen = gen; j.gsrc = gsrc; j.gwrite = gwrite; j.grow0 = row0; return j; };
+            auto gather_f = [&](int k_offset, int rows_per_warp) {
+                Job j = Builder::zero();
+                j.type = J_GATHER; j.M = B; j.C = e->xs; j.out0 = nullptr; j.out1 = nullptr; j.ldc = ldx; j.out2 = e->s2buf; j.ldb = lds;
+                j.out3 = e->rd; j.i0 = rows_per_warp; j.k_offset = k_offset; j.stg = 4 | 8;
+                j.ntiles = (B + kRowsWarp * rows_per_warp - 1) / (kRowsWarp * rows_per_warp);
+                return j; };
+            // online critic forward on [s|a] of update k + k_offset, rows [row0, row0 + nrows)
+            auto cl1_q = [&](int k_offset, int row0, int nrows) {
+                Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, nullptr, 2 * H1, H1, PC + L.critic_w1[0], H1, sW1,
+                               e->ch2 + (size_t)row0 * 2 * H2, 2 * H2, H2, nrows, H2, H1, 2);
+                j.bias = PC + L.critic_b1[0]; j.sBias = H2; j.aux0 = PC + L.critic_w2[0]; j.sAux = H2;
+                j.out0 = e->qpart + row0; j.i0 = B; j.b_static = 1; j.k_offset = k_offset;
+                return gen_job(j, GEN_L0, 3, 1, row0); };
+            auto reduce_q = [&]() {
+                Job j = Builder::zero();
+                j.type = J_REDUCE_Q; j.A = e->lparts_q; j.i0 = RB; j.out0 = e->loss_scalar; j.out1 = GC + L.critic_b2[0];
+                j.out2 = GC + L.critic_b2[1]; j.ntiles = 1;
+                if (fuse_adam) {
+                    j.adam = 2; j.aux0 = PC + L.critic_b2[0]; j.aux1 = e->mc + L.critic_b2[0]; j.aux2 = e->vc + L.critic_b2[0];
+                    j.aux3 = PT + L.critic_b2[0]; j.sAux = (long long)(L.critic_b2[1] - L.critic_b2[0]);
+                }
+                return j; };
+            auto st = [](Job j) { j.b_static = 1; return j; };
+            const int cw = 256;                                        // columns per tile of the partial-sum reductions
+
+            e->p_fold.begin = (int)e->phases.size();
+            { int p0 = b.phase(); e->phases[p0].pad = 1; b.add(gather_f(0, 1)); }
+            { int p0 = b.phase(); e->phases[p0].pad = 1; b.add(cl1_q(0, 0, B)); }
+            {   // F1
+                b.phase();
+                Job j = b.gemm(G_FWD, E_BIAS_RELU, nullptr, H1, 0, PA + L.actor_w1, H1, 0, e->ah2, H2, 0, B, H2, H1, 1);
+                j.bias = PA + L.actor_b1; j.b_static = 0;              // W1 was stepped by the previous phase (F8 of update k-1)
+                j.i1 = 2 * A; j.aux1 = PA + L.actor_w_mu; j.i2 = H2; j.i3 = 0; j.out1 = e->hpart; j.i0 = B;
+                b.add(gen_job(j, GEN_L0, 0, 1));
+            }
+            {   // F2
+                b.phase();
+                Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, nullptr, 2 * H1, H1, PT + L.critic_w1[0], H1, sW1, e->th2, 2 * H2, H2, B, H2, H1, 2);
+                j.bias = PT + L.critic_b1[0]; j.sBias = H2; j.aux0 = PT + L.critic_w2[0]; j.sAux = H2;
+                j.out0 = e->qtpart; j.i0 = B; j.b_static = 1;
+                b.add(gen_job(j, GEN_L0, 1, 0));
+            }
+            {   // F3
+                b.phase();
+                Job j = b.gemm(G_DX, E_MASK, e->ch2, 2 * H2, H2, PC + L.critic_w1[0], H1, sW1, e->dh1, 2 * H1, H1, B, H1, H2, 2);
+                j.mask = e->ch1; j.ldmask = 2 * H1; j.sMask = H1; j.b_static = 1;
+                j.colp = e->colp_b0; j.ldcolp = 2 * H1;
+                b.add(gen_job(j, GEN_BACKUP, 0, 0));
+            }
+            {   // F4: the light jobs come first, so that the CTAs that get a second tile (148 < tiles) pair a light tile with a dW0 tile
+                b.phase();
+                b.add(reduce_q());
+                b.add(with_adam(b.colsum(e->colp_b1, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, RB, 2 * H2, 1, cw), true));
+                b.add(with_adam(b.colsum(e->colp_w2, 2 * H2, 0, nullptr, 0, GC + L.critic_w2[0], 0, RB, 2 * H2, 1, cw), true));
+                b.add(with_adam(b.colsum(e->colp_b0, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, RB, 2 * H1, 1, cw), true));
+                b.add(st(with_adam(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2), true)));
+                Job j = st(with_adam(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1), true));
+                j.stg = 16;                                              // xs of this update's parity
+                b.add(j);
+            }
+            if (!fuse_adam) { b.phase(); if (e->peer_mode) b.add(peer_signal(true)); b.add(adam(true)); }
+            {   // F5
+                b.phase();
+                Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, nullptr, 2 * H1, H1, PC + L.critic_w1[0], H1, sW1, e->cp2, 2 * H2, H2, B, H2, H1, 2);
+                j.bias = PC + L.critic_b1[0]; j.sBias = H2; j.aux0 = PC + L.critic_w2[0]; j.sAux = H2;
+                j.out0 = e->qppart; j.i0 = B; j.b_static = 0;          // critic weights were just stepped
+                b.add(gen_job(j, GEN_L0, 2, 1));
+                b.add(gather_f(1, 2));
+            }
+            {   // F6
+                b.phase();
+                Job j = b.gemm(G_DX, E_MASK, e->cp2, 2 * H2, H2, PC + L.critic_w1[0], H1, sW1, e->dh1, 2 * H1, H1, B, H1, H2, 2);
+                j.mask = e->cp1; j.ldmask = 2 * H1; j.sMask = H1; j.b_static = 1;
+                j.i1 = A; j.aux1 = PC + L.critic_w0[0] + O; j.i2 = OA; j.i3 = 1; j.sAux = (long long)H1 * OA; j.out1 = e->dpart; j.i0 = B;
+                b.add(gen_job(j, GEN_PI, 0, 0));
+            }
+            // rows of next update's C.L1 that fit beside A.dh1 in F7 (one round = one tile per SM); the rest rides in F8
+            const int t_adh1 = RB * tnH1;
+            int blocks7 = (cap - t_adh1 - 1) / (2 * e->tnH2);
+            if (blocks7 < 0) blocks7 = 0;
+            if (blocks7 > RB) blocks7 = RB;
+            const int rows7 = blocks7 * kBM < B ? blocks7 * kBM : B;
+            {   // F7
+                b.phase();
+                Job j = b.gemm(G_DX, E_MASK, e->ah2, H2, 0, PA + L.actor_w1, H1, 0, e->adh1, H1, 0, B, H1, H2, 1);
+                j.mask = e->ah1; j.ldmask = H1; j.b_static = 1;
+                j.colp = e->colp_ab0; j.ldcolp = H1;
+                b.add(gen_job(j, GEN_GHEAD, 0, 0));
+                Job r = Builder::zero();
+                r.type = J_REDUCE_PI; r.A = e->lparts_pi; r.i0 = RB; r.out0 = e->loss_scalar + 1; r.ntiles = 1;
+                b.add(r);
+                if (rows7 > 0) b.add(cl1_q(1, 0, rows7));
+            }
+            int last = 0;
+            {   // F8
+                last = b.phase();
+                b.add(st(with_adam(b.gemm(G_DW, E_STORE, e->adh2, H2, 0, e->ah1, H1, 0, GA + L.actor_w1, H1, 0, H2, H1, B, 1), false)));
+                b.add(st(with_adam(b.gemm(G_DW, E_STORE, e->ghead, ldh, 0, e->ah2, H2, 0, GA + L.actor_w_mu, H2, 0, 2 * A, H2, B, 1), false)));
+                Job j = st(with_adam(b.gemm(G_DW, E_STORE, e->adh1, H1, 0, e->s2buf, lds, 0, GA + L.actor_w0, O, 0, H1, O, B, 1), false));
+                j.stg = 2;
+                b.add(j);
+                b.add(with_adam(b.colsum(e->colp_ab1, H2, 0, nullptr, 0, GA + L.actor_b1, 0, RB, H2, 1, cw), false));
+                b.add(with_adam(b.colsum(e->colp_ab0, H1, 0, nullptr, 0, GA + L.actor_b0, 0, RB, H1, 1, cw), false));
+                b.add(with_adam(b.colsum(e->colp_bh, 16, 0, nullptr, 0, GA + L.actor_b_mu, 0, RB, 2 * A, 1, 32), false));
+                if (rows7 < B) b.add(cl1_q(1, rows7, B - rows7));
+            }
+            if (!fuse_adam) {
+                last = b.phase();
+                if (e->peer_mode && actor_sync) b.add(peer_signal(false));
+                Job j = adam(false); if (!actor_sync) j.i2 = 0; b.add(j);
+            }
+            (void)last;
+            e->p_fold.end = (int)e->phases.size();
+            e->fold_ok = true;
+        }
     }
 }
