@@ -40,13 +40,14 @@ __device__ __forceinline__ void heads_from_partials(const FoldPtrs& f, int A, in
 // ----------------------------------------------------------------------------------------------------------
 // GEN_L0
 // ----------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* smem, int i0, int i_valid, int z, bool col0, int kk) {
+__device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* smem, int i0, int i_valid, int z, bool col0, int kk) {
     const FoldPtrs& f = ra.f;
     float* gsm = smem + kPipeFloats;
     float* XsT = gsm + kGenXT;
     float* W0s = gsm + kGenW0;
     const int t = threadIdx.x;
-    const int src = jb.gsrc, O = ra.O, A = ra.A, B = ra.B;
+    // (job fields live in shared memory: copy what the loops use into registers, stores through float* could alias them)
+    const int src = jb.gsrc, O = ra.O, A = ra.A, B = ra.B, gwrite = jb.gwrite;
     const int K0 = src == 0 ? O : O + A;
     const int H1 = jb.K;
     const int pitchW = K0 | 1;
@@ -138,7 +139,7 @@ __device__ __noinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* sme
             }
         }
         float* col = stage_a(smem, n >> 6) + (n & 63);
-        const bool wr_out = col0 && jb.gwrite && Hout != nullptr && n < H1;
+        const bool wr_out = col0 && gwrite && Hout != nullptr && n < H1;
 #pragma unroll
         for (int m = 0; m < 32; ++m) {
             const float h = (n < H1 && m < i_valid) ? fmaxf(acc[m] + bias, 0.f) : 0.f;
@@ -153,12 +154,13 @@ __device__ __noinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* sme
 // GEN_BACKUP / GEN_PI: the loss rows (row_loss_tile) computed per tile, dh2 generated in place over the relu-mask tile
 // ----------------------------------------------------------------------------------------------------------
 template <bool IS_PI>
-__device__ __noinline__ void gen_loss(const Job& jb, const RunArgs& ra, float* smem, int i0, int i_valid, int z, int ti, bool col0, int k) {
+__device__ __forceinline__ void gen_loss(const Job& jb, const RunArgs& ra, float* smem, int i0, int i_valid, int z, int ti, bool col0, int k) {
     const FoldPtrs& f = ra.f;
     float* misc = smem + kPipeFloats + kGenMisc;
     float* dqs = misc;                                      // [2][32]
     const int t = threadIdx.x;
     const int H2 = jb.K, B = ra.B, nt = f.tnH2;
+    float* const dh2g = f.dh2; float* const colp_b1 = f.colp_b1; float* const colp_w2 = f.colp_w2;
     const size_t par = (size_t)(k & 1);
     // relu-mask tile (forward activations of layer 1, this z) -> the A stage buffers
     {
@@ -255,14 +257,14 @@ __device__ __noinline__ void gen_loss(const Job& jb, const RunArgs& ra, float* s
             const float v = (ok && h > 0.f) ? d * w2 : 0.f;
             col[m * kPitchRC] = v;
             if (wr && m < i_valid) {
-                f.dh2[(size_t)(i0 + m) * 2 * H2 + (size_t)z * H2 + n] = v;
+                dh2g[(size_t)(i0 + m) * 2 * H2 + (size_t)z * H2 + n] = v;
                 cs_b1 += v;
                 cs_w2 = fmaf(d, h, cs_w2);
             }
         }
         if (wr) {
-            f.colp_b1[(size_t)ti * 2 * H2 + (size_t)z * H2 + n] = cs_b1;      // partial of d loss / d b1[z][n]
-            f.colp_w2[(size_t)ti * 2 * H2 + (size_t)z * H2 + n] = cs_w2;      // partial of d loss / d W2[z][n]
+            colp_b1[(size_t)ti * 2 * H2 + (size_t)z * H2 + n] = cs_b1;        // partial of d loss / d b1[z][n]
+            colp_w2[(size_t)ti * 2 * H2 + (size_t)z * H2 + n] = cs_w2;        // partial of d loss / d W2[z][n]
         }
     }
     __syncthreads();
@@ -271,11 +273,12 @@ __device__ __noinline__ void gen_loss(const Job& jb, const RunArgs& ra, float* s
 // ----------------------------------------------------------------------------------------------------------
 // GEN_GHEAD: head-gradient rows (row_ghead_tile) + the back-projection dh2 = (g . Wh) * relu'(h2)
 // ----------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void gen_ghead(const Job& jb, const RunArgs& ra, float* smem, int i0, int i_valid, int ti, bool col0, int k) {
+__device__ __forceinline__ void gen_ghead(const Job& jb, const RunArgs& ra, float* smem, int i0, int i_valid, int ti, bool col0, int k) {
     const FoldPtrs& f = ra.f;
     float* ghs = smem + kPipeFloats + kGenMisc;            // [32][16]
     const int t = threadIdx.x;
     const int H2 = jb.K, A = ra.A, B = ra.B, twoA = 2 * A;
+    float* const adh2g = f.adh2;
     {
         const int nst = (H2 + kBK - 1) / kBK;
         for (int s = 0; s < nst; ++s) load_operand<true>(stage_a(smem, s), jb.A, jb.lda, i0, i_valid, s * kBK, min(kBK, H2 - s * kBK), jb.a_vec);
@@ -331,7 +334,7 @@ __device__ __noinline__ void gen_ghead(const Job& jb, const RunArgs& ra, float* 
                 if (j < twoA) v = fmaf(ghs[m * 16 + j], wh[j], v);
             v = (n < H2 && m < i_valid && h > 0.f) ? v : 0.f;
             col[m * kPitchRC] = v;
-            if (wr && m < i_valid) { f.adh2[(size_t)(i0 + m) * H2 + n] = v; cs += v; }
+            if (wr && m < i_valid) { adh2g[(size_t)(i0 + m) * H2 + n] = v; cs += v; }
         }
         if (wr) f.colp_ab1[(size_t)ti * H2 + n] = cs;        // partial of d loss / d b1[n] (actor)
     }
