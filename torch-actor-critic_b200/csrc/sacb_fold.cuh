@@ -40,6 +40,15 @@ __device__ __forceinline__ void heads_from_partials(const FoldPtrs& f, int A, in
 // ----------------------------------------------------------------------------------------------------------
 // GEN_L0
 // ----------------------------------------------------------------------------------------------------------
+// shared-memory address of the generators' mbarrier (the tcgen05 path's first mbarrier slot; unused by this kernel variant)
+__device__ __forceinline__ unsigned gen_mbar_addr(float* smem) {
+    return smem_u32(reinterpret_cast<char*>(smem) + (kPipeFloats + kGenFloats) * 4 + kJobsBytes + kMaxPhases * (int)sizeof(Phase));
+}
+
+// Register tile of the generators' small products: thread t owns rows 8*(t/64) .. +7 and columns (t%64) + 64*j, j = 0..3
+// (j = the stage buffer the column lives in), so the row operands are warp-wide broadcasts and the column operands are
+// conflict-free, and every shared-memory value is reused 4x / 8x from registers.
+
 __device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* smem, int i0, int i_valid, int z, bool col0, int kk) {
     const FoldPtrs& f = ra.f;
     float* gsm = smem + kPipeFloats;
@@ -63,26 +72,47 @@ __device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* 
         default: W0g = f.c_w0 + (size_t)z * H1 * K0; b0g = f.c_b0 + z * H1; Xg = f.xs + par * f.xs_stride; ldX = f.ldx; ncopy = K0;
                 Hout = f.ch1 + z * H1; ldH = 2 * H1; break;
     }
-    // 1. layer-0 weights of this tile's net -> smem [H1][pitchW] (odd pitch: the FFMA loop's column reads hit 32 banks)
-    {
-        const int n_el = H1 * K0;
-        if (pitchW == K0 && ((reinterpret_cast<uintptr_t>(W0g) & 15) == 0)) {
-            const int n16 = n_el >> 2;
-            for (int v = t; v < n16; v += kThreads) cp_async16(W0s + 4 * v, W0g + 4 * v, 16);
-            for (int e = (n16 << 2) + t; e < n_el; e += kThreads) cp_async4(W0s + e, W0g + e);
-        } else {
-            for (int e = t; e < n_el; e += kThreads) {
-                const int n = e / K0, k = e - n * K0;
-                cp_async4(W0s + n * pitchW + k, W0g + e);
-            }
+    // 1. layer-0 weights of this tile's net -> smem [H1][pitchW] (odd pitch: the FFMA loop's column reads hit 32 banks).
+    //    The matrix is one contiguous block of the arena: ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) issued by one thread,
+    //    completion on an mbarrier -- instead of 6 LDGSTS per thread.  Unaligned / even-K0 shapes fall back to cp.async.
+    const int n_el = H1 * K0;
+    const bool bulk = pitchW == K0 && ((reinterpret_cast<uintptr_t>(W0g) & 15) == 0) && ((n_el & 3) == 0);
+    const unsigned mbar = gen_mbar_addr(smem);
+    if (bulk) {
+        if (t == 0) {
+            const unsigned bytes = (unsigned)n_el * 4u;
+            mbar_init(mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy reads of W0s are done (block barrier)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(W0s)), "l"(W0g), "r"(bytes), "r"(mbar) : "memory");
+        }
+    } else {
+        for (int e = t; e < n_el; e += kThreads) {
+            const int n = e / K0, k = e - n * K0;
+            cp_async4(W0s + n * pitchW + k, W0g + e);
         }
         cp_async_commit();
     }
-    // 2. input rows, transposed: XsT[k][m]
-    for (int e = t; e < 32 * ncopy; e += kThreads) {
-        const int m = e / ncopy, c = e - m * ncopy;
-        XsT[c * 32 + m] = m < i_valid ? __ldcg(Xg + (size_t)(row0 + m) * ldX + c) : 0.f;
+    TR(130);
+    // 2. input rows, transposed: XsT[k][m] (all loads in flight before the first store)
+    {
+        float xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = t + u * kThreads;
+            const int m = e / ncopy, c = e - m * ncopy;
+            xv[u] = (e < 32 * ncopy && m < i_valid) ? __ldcg(Xg + (size_t)(row0 + m) * ldX + c) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = t + u * kThreads;
+            const int m = e / ncopy, c = e - m * ncopy;
+            if (e < 32 * ncopy) XsT[c * 32 + m] = xv[u];
+        }
     }
+    TR(131);
     // 2b. action columns = the policy's own sample (networks/linear.py:37-51): pass 0 (a2, eps1) for the target critic,
     //     pass 1 (pi, eps2) for the critic of the actor loss.  8 lanes per row, lane a < A.
     if (src == 1 || src == 2) {
@@ -116,35 +146,52 @@ __device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* 
             }
         }
     }
-    const int n = t;                                       // this thread's output column (H1 <= kThreads)
-    const float bias = n < H1 ? __ldcg(b0g + n) : 0.f;
-    cp_async_wait<0>();
-    __syncthreads();
+    TR(132);
+    const int cg = t & 63, rg = t >> 6;                     // this thread's column group / row group (kThreads == 256)
+    float bias[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bias[j] = (cg + 64 * j < H1) ? __ldcg(b0g + cg + 64 * j) : 0.f;
+    if (!bulk) cp_async_wait<0>();
+    __syncthreads();                                        // X^T complete; the mbarrier's init is visible to every thread
+    if (bulk) mbar_wait(mbar, 0);
+    TR(133);
     // 3. h1[m][n] = relu(b0[n] + x[m] . W0[n]) for the tile's 32 rows, fp32 FFMA, k ascending
-    const int H1r = (H1 + 7) & ~7;
-    if (n < H1r) {
-        float acc[32];
+    float acc[8][4];
 #pragma unroll
-        for (int m = 0; m < 32; ++m) acc[m] = 0.f;
-        if (n < H1) {
-            const float* wr = W0s + n * pitchW;
-            for (int k = 0; k < K0; ++k) {
-                const float w = wr[k];
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 x = *reinterpret_cast<const float4*>(XsT + k * 32 + 4 * q);
-                    acc[4 * q + 0] = fmaf(x.x, w, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(x.y, w, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(x.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x.w, w, acc[4 * q + 3]);
-                }
-            }
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    {
+        // columns beyond H1 read (finite) stale shared memory and are masked below
+        const float* w0 = W0s + cg * pitchW;
+        const int cstride = 64 * pitchW;
+        const float* xr = XsT + 8 * rg;
+#pragma unroll 1
+        for (int k = 0; k < K0; ++k) {
+            const float4 xa = *reinterpret_cast<const float4*>(xr + k * 32);
+            const float4 xb = *reinterpret_cast<const float4*>(xr + k * 32 + 4);
+            const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            float w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = (cg + 64 * j < H1) ? w0[j * cstride + k] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x[i], w[j], acc[i][j]);
         }
-        float* col = stage_a(smem, n >> 6) + (n & 63);
-        const bool wr_out = col0 && gwrite && Hout != nullptr && n < H1;
+    }
+    TR(134);
+    const bool wr_out = col0 && gwrite && Hout != nullptr;
 #pragma unroll
-        for (int m = 0; m < 32; ++m) {
-            const float h = (n < H1 && m < i_valid) ? fmaxf(acc[m] + bias, 0.f) : 0.f;
+    for (int j = 0; j < 4; ++j) {
+        const int n = cg + 64 * j;
+        float* col = stage_a(smem, j) + cg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = 8 * rg + i;
+            const float h = (n < H1 && m < i_valid) ? fmaxf(acc[i][j] + bias[j], 0.f) : 0.f;
             col[m * kPitchRC] = h;
-            if (wr_out && m < i_valid) Hout[(size_t)(row0 + m) * ldH + n] = h;
+            if (wr_out && n < H1 && m < i_valid) Hout[(size_t)(row0 + m) * ldH + n] = h;
         }
     }
     __syncthreads();
@@ -165,10 +212,12 @@ __device__ __forceinline__ void gen_loss(const Job& jb, const RunArgs& ra, float
     // relu-mask tile (forward activations of layer 1, this z) -> the A stage buffers
     {
         const float* Ag = jb.A + (size_t)z * jb.sA;
+        const int lda = jb.lda, a_vec = jb.a_vec;
         const int nst = (H2 + kBK - 1) / kBK;
-        for (int s = 0; s < nst; ++s) load_operand<true>(stage_a(smem, s), Ag, jb.lda, i0, i_valid, s * kBK, min(kBK, H2 - s * kBK), jb.a_vec);
+        for (int s = 0; s < nst; ++s) load_operand<true>(stage_a(smem, s), Ag, lda, i0, i_valid, s * kBK, min(kBK, H2 - s * kBK), a_vec);
         cp_async_commit();
     }
+    TR(120);
     // per-row scalars: 8 lanes per row (lane tt sums partial tile tt of every net), all loads of the tile in flight at once
     const float Bf = (float)B;
     float* rowv = misc + 64;                                // [32][4] per-row loss terms
@@ -234,32 +283,45 @@ __device__ __forceinline__ void gen_loss(const Job& jb, const RunArgs& ra, float
             rowv[m * 4 + 0] = v0; rowv[m * 4 + 1] = v1; rowv[m * 4 + 2] = IS_PI ? 0.f : dq1; rowv[m * 4 + 3] = IS_PI ? 0.f : dq2;
         }
     }
+    TR(121);
     const int n = t;
     const float w2 = n < H2 ? __ldcg(f.c_w2 + (size_t)z * H2 + n) : 0.f;
     cp_async_wait<0>();
     __syncthreads();
+    TR(122);
     if (col0 && z == 0 && t < 4) {                          // fixed summation order over the tile's rows (deterministic losses)
         float s = 0.f;
+#pragma unroll 4
         for (int m = 0; m < 32; ++m) s += rowv[m * 4 + t];
         (IS_PI ? f.lparts_pi : f.lparts_q)[(size_t)ti * 4 + t] = s;
     }
     const int H2r = (H2 + 7) & ~7;
     if (n < H2r) {
         float* col = stage_a(smem, n >> 6) + (n & 63);
-        const float* dq = dqs + z * 32;
         const bool wr = !IS_PI && col0 && n < H2;
+        // Rolled on purpose: this code runs once per tile, i.e. from a cold instruction cache -- a fully unrolled version of
+        // this loop (650 instructions) measured 6.3k cycles, the instruction fetch of 10 KB of straight-line code.
+        // 4 rows per iteration, every shared-memory load before the first store (col[] and dq[] may alias for the compiler).
         float cs_b1 = 0.f, cs_w2 = 0.f;
-#pragma unroll 8
-        for (int m = 0; m < 32; ++m) {
-            const float h = col[m * kPitchRC];
-            const bool ok = n < H2 && m < i_valid;
-            const float d = dq[m];
-            const float v = (ok && h > 0.f) ? d * w2 : 0.f;
-            col[m * kPitchRC] = v;
-            if (wr && m < i_valid) {
-                dh2g[(size_t)(i0 + m) * 2 * H2 + (size_t)z * H2 + n] = v;
-                cs_b1 += v;
-                cs_w2 = fmaf(d, h, cs_w2);
+        const float* dqz = dqs + z * 32;
+#pragma unroll 1
+        for (int m0 = 0; m0 < 32; m0 += 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dqz + m0);
+            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+            float h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) h[u] = col[(m0 + u) * kPitchRC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int m = m0 + u;
+                const bool ok = n < H2 && m < i_valid;
+                const float v = (ok && h[u] > 0.f) ? d[u] * w2 : 0.f;
+                col[m * kPitchRC] = v;
+                if (wr && m < i_valid) {
+                    dh2g[(size_t)(i0 + m) * 2 * H2 + (size_t)z * H2 + n] = v;
+                    cs_b1 += v;
+                    cs_w2 = fmaf(d[u], h[u], cs_w2);
+                }
             }
         }
         if (wr) {
@@ -280,10 +342,19 @@ __device__ __forceinline__ void gen_ghead(const Job& jb, const RunArgs& ra, floa
     const int H2 = jb.K, A = ra.A, B = ra.B, twoA = 2 * A;
     float* const adh2g = f.adh2;
     {
+        const float* Ag = jb.A;
+        const int lda = jb.lda, a_vec = jb.a_vec;
         const int nst = (H2 + kBK - 1) / kBK;
-        for (int s = 0; s < nst; ++s) load_operand<true>(stage_a(smem, s), jb.A, jb.lda, i0, i_valid, s * kBK, min(kBK, H2 - s * kBK), jb.a_vec);
+        for (int s = 0; s < nst; ++s) load_operand<true>(stage_a(smem, s), Ag, lda, i0, i_valid, s * kBK, min(kBK, H2 - s * kBK), a_vec);
         cp_async_commit();
     }
+    const int cg = t & 63, rg = t >> 6;
+    // head weights of this thread's 4 columns: wh[j][c] = Wh[j][cg + 64 c]
+    float wh[16][4];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wh[j][c] = (j < twoA && cg + 64 * c < H2) ? __ldcg(f.a_wh + (size_t)j * H2 + cg + 64 * c) : 0.f;
     if (t < 256) {
         const int m = t >> 3, a = t & 7, row = i0 + m;
         if (a < A) {
@@ -293,13 +364,12 @@ __device__ __forceinline__ void gen_ghead(const Job& jb, const RunArgs& ra, floa
                 const float glogp = ra.alpha / (float)B;
                 const float mu = __ldcg(f.heads + (size_t)row * f.ldh + a), lsr = __ldcg(f.heads + (size_t)row * f.ldh + A + a);
                 const float e = eps ? __ldg(eps + (size_t)row * A + a) : 0.f;
-                float dpi = 0.f, pp[8];
-                for (int t0 = 0; t0 < f.tnH1x2; t0 += 8) {
+                float pp[16];                               // d pi partials: every load in flight at once, summed in tile order
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) pp[u] = (t0 + u < f.tnH1x2) ? __ldcg(f.dpart + ((size_t)(t0 + u) * A + a) * B + row) : 0.f;
+                for (int u = 0; u < 16; ++u) pp[u] = (u < f.tnH1x2) ? __ldcg(f.dpart + ((size_t)u * A + a) * B + row) : 0.f;
+                float dpi = 0.f;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) dpi += pp[u];
-                }
+                for (int u = 0; u < 16; ++u) dpi += pp[u];
                 const HeadVals h = head_eval(mu, lsr, e, eps == nullptr, ra);
                 const float dcorr = (ra.flags & 1u) ? 2.f * h.th : h.th;
                 gu = dpi * ra.act_limit * (1.f - h.th * h.th) + glogp * dcorr;
@@ -309,36 +379,53 @@ __device__ __forceinline__ void gen_ghead(const Job& jb, const RunArgs& ra, floa
             }
             ghs[m * 16 + a] = gu; ghs[m * 16 + A + a] = gls;
         }
+        if (a == 7)
+            for (int j = twoA; j < 16; ++j) ghs[m * 16 + j] = 0.f;    // unused tail of the row: finite (it meets zero weights)
     }
-    const int n = t;
-    float wh[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) wh[j] = (j < twoA && n < H2) ? __ldcg(f.a_wh + (size_t)j * H2 + n) : 0.f;
+    TR(141);
     cp_async_wait<0>();
     __syncthreads();
+    TR(142);
     if (col0 && t < twoA) {                                 // partial of d loss / d b_heads[t]
         float s = 0.f;
         for (int m = 0; m < 32; ++m) s += ghs[m * 16 + t];
         f.colp_bh[(size_t)ti * 16 + t] = s;
     }
-    const int H2r = (H2 + 7) & ~7;
-    if (n < H2r) {
-        float* col = stage_a(smem, n >> 6) + (n & 63);
-        const bool wr = col0 && n < H2;
-        float cs = 0.f;
-        for (int m = 0; m < 32; ++m) {
-            const float h = col[m * kPitchRC];
-            float v = 0.f;
+    // dh2 for rows 8*rg .. +7, columns cg + 64c: g rows are warp-wide broadcasts reused for 4 columns from registers.
+    // One row per iteration, rolled (cold instruction cache, see gen_loss).
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int m = 8 * rg + i;
+        const float* gr = ghs + m * 16;
+        const float4 g0 = *reinterpret_cast<const float4*>(gr), g1 = *reinterpret_cast<const float4*>(gr + 4),
+                     g2 = *reinterpret_cast<const float4*>(gr + 8), g3 = *reinterpret_cast<const float4*>(gr + 12);
+        const float g[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
+        float hv[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j < twoA) v = fmaf(ghs[m * 16 + j], wh[j], v);
-            v = (n < H2 && m < i_valid && h > 0.f) ? v : 0.f;
-            col[m * kPitchRC] = v;
-            if (wr && m < i_valid) { adh2g[(size_t)(i0 + m) * H2 + n] = v; cs += v; }
+        for (int c = 0; c < 4; ++c) hv[c] = (stage_a(smem, c) + cg)[m * kPitchRC];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a = fmaf(g[j], wh[j][c], a);   // j ascending; entries beyond 2A are zero
+            const int n = cg + 64 * c;
+            const float o = (n < H2 && m < i_valid && hv[c] > 0.f) ? a : 0.f;
+            (stage_a(smem, c) + cg)[m * kPitchRC] = o;
+            if (col0 && n < H2 && m < i_valid) { adh2g[(size_t)(i0 + m) * H2 + n] = o; cs[c] += o; }
         }
-        if (wr) f.colp_ab1[(size_t)ti * H2 + n] = cs;        // partial of d loss / d b1[n] (actor)
+    }
+    if (col0) {
+        // partial of d loss / d b1[n] (actor): the 4 row groups of a column meet in shared memory, fixed order
+        float* csum = smem + kPipeFloats + kGenXT;          // [4][256] (the X^T scratch is idle in this generator)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) csum[rg * 256 + cg + 64 * c] = cs[c];
     }
     __syncthreads();
+    if (col0 && t < H2) {
+        const float* csum = smem + kPipeFloats + kGenXT;
+        f.colp_ab1[(size_t)ti * H2 + t] = (csum[t] + csum[256 + t]) + (csum[512 + t] + csum[768 + t]);
+    }
 }
 
 }  // namespace sacb
