@@ -196,6 +196,83 @@ int sacb_set_precision(sacb_handle h, int32_t tf32x3);
 /* Execution mode: 0 = persistent cooperative kernel (default), 1 = one launch per phase (debug / profiling). */
 int sacb_set_mode(sacb_handle h, int32_t mode);
 
+/* =====================================================================================================================
+ * Visual SAC (BASELINE configs[4]): the reference's networks/convolutional.py + buffer/visual_replay_buffer.py path.
+ *
+ * Same conventions as above (status codes, caller-owned device pointers, stream as uintptr_t, no CPU fallback); messages
+ * of failing sacv_* calls are read with sacv_last_error().  A handle owns one (VisualActor, VisualDoubleCritic, target)
+ * triple's workspace for a fixed batch size.  Frames live in the replay ring as uint8 [N, C, H, W] (the reference keeps
+ * float tensors of raw 0..255 pixels, environments/wall_runner.py:54-58; integral pixel values survive the uint8 ring
+ * unchanged) and are gathered straight into im2col form; explicit batches (sacv_load_batch, forward calls) pass float32
+ * frames like the reference's VisualBatch / MultiObservation.
+ * ===================================================================================================================== */
+typedef struct sacv_config {
+    uint32_t struct_size;          /* = sizeof(sacv_config) */
+    int32_t device;
+    int32_t obs_dim, act_dim;      /* feature width O (environments/wall_runner.py:21: 168), action width A (56) */
+    int32_t hidden1, hidden2;      /* MLP widths (main.py:61) */
+    int32_t batch_size;
+    int32_t vis_c, vis_h, vis_w;   /* frame shape (main.py:68 uses 3x64x64; BASELINE configs[4] 3x84x84) */
+    int32_t filters[3], kernels[3], strides[3];   /* simple_cnn, networks/convolutional.py:32-44 (main.py:65-67: 32/64/64, 8/4/3, 4/2/1) */
+    int32_t dense;                 /* simple_cnn dense_size (512) */
+    float log_min_std, log_max_std, act_limit;
+    int32_t precision;             /* GEMM arithmetic: 1 = 3xTF32 (fp32-level accuracy, default), 0 = plain TF32 */
+    double alpha, gamma, polyak, reward_scale, lr_pi, lr_q, beta1, beta2, adam_eps;
+    uint32_t flags;                /* SACB_FLAG_CANONICAL_LOGPROB */
+    uint32_t reserved0;
+    uint64_t seed;
+} sacv_config;
+
+/* Offsets (floats) inside the flat arenas.  Actor arena: trunk, CNN block, heads ([mu ; log_std] as one [2A, H2+1] matrix,
+ * convolutional.py:78-79).  Critic arena: q1 net then q2 net, `critic_net_floats` apart, each: MLP [O+A,H1,H2,1], final
+ * Linear(2,1), CNN block (convolutional.py:140-143).  cnn_* are relative to the start of a CNN block. */
+typedef struct sacv_layout_info {
+    int64_t actor_floats, a_l0w, a_l0b, a_l1w, a_l1b, a_cnn, a_muw, a_lsw, a_mub, a_lsb;
+    int64_t critic_floats, critic_net_floats, c_l0w, c_l0b, c_l1w, c_l1b, c_l2w, c_l2b, c_fw, c_fb, c_cnn;
+    int64_t cnn_floats, cnn_w[3], cnn_b[3], cnn_lw, cnn_lb, cnn_fw, cnn_fb;
+    int32_t conv_h[3], conv_w[3], flat, reserved0;      /* calculate_size, convolutional.py:14-29 */
+} sacv_layout_info;
+
+typedef struct sacv_engine* sacv_handle;
+
+const char* sacv_last_error(void);
+int sacv_layout(const sacv_config* cfg, sacv_layout_info* out);
+int sacv_create(const sacv_config* cfg, sacv_handle* out);
+int sacv_destroy(sacv_handle h);
+int sacv_bind_params(sacv_handle h, float* actor_dev, float* critic_dev, float* target_dev);
+int sacv_bind_adam(sacv_handle h, float* m_actor, float* v_actor, int64_t step_actor, float* m_critic, float* v_critic, int64_t step_critic);
+int sacv_get_adam_steps(sacv_handle h, int64_t* step_actor, int64_t* step_critic);
+int sacv_set_scalar(sacv_handle h, const char* name, double value);      /* alpha gamma polyak reward_scale lr_pi lr_q beta1 beta2 adam_eps precision */
+
+/* VisualReplayBuffer.__init__ / store / sample (buffer/visual_replay_buffer.py:21-66).  Ring arrays (device): features
+ * [N,O] f32, frames [N,C,H,W] u8, actions [N,A] f32, rewards [N] f32, next_features, next_frames, done [N] u8. */
+int sacv_bind_buffer(sacv_handle h, float* features, uint8_t* frames, float* actions, float* rewards, float* next_features,
+                     uint8_t* next_frames, uint8_t* done, int64_t capacity);
+int sacv_buffer_state(sacv_handle h, int64_t* ptr, int64_t* size, int64_t* capacity);
+int sacv_set_buffer_state(sacv_handle h, int64_t ptr, int64_t size);
+int sacv_store(sacv_handle h, const float* features_host, const uint8_t* frames_host, const float* actions_host, const float* rewards_host,
+               const float* next_features_host, const uint8_t* next_frames_host, const uint8_t* done_host, int64_t count, uintptr_t stream);
+int sacv_sample(sacv_handle h, int32_t batch, const int64_t* idx_dev_or_null, float* features, float* frames_f32, float* actions, float* rewards,
+                float* next_features, float* next_frames_f32, float* done, int64_t* idx_out_or_null, uintptr_t stream);
+
+/* n_updates x (VisualReplayBuffer.sample -> SAC.update_critic -> SAC.update_policy -> update_targets), sac/algorithm.py:274-278;
+ * idx [n,B] / eps [n,2,B,A] may be injected (device) or null (drawn on the device). */
+int sacv_update(sacv_handle h, int32_t n_updates, const int64_t* idx_dev_or_null, const float* eps_dev_or_null, float* loss_q_dev,
+                float* loss_pi_dev, uintptr_t stream);
+/* piecewise API on an explicit VisualBatch (sac/algorithm.py:115-162,77-81) */
+int sacv_load_batch(sacv_handle h, const float* features, const float* frames_f32, const float* actions, const float* rewards,
+                    const float* next_features, const float* next_frames_f32, const float* done, uintptr_t stream);
+int sacv_update_critic(sacv_handle h, const float* eps_dev_or_null, float* loss_q_dev, uintptr_t stream);
+int sacv_update_policy(sacv_handle h, const float* eps_dev_or_null, float* loss_pi_dev, uintptr_t stream);
+int sacv_update_targets(sacv_handle h, uintptr_t stream);
+/* VisualActor.forward / VisualDoubleCritic.forward (networks/convolutional.py:85-121,144-183) on n <= batch_size rows */
+int sacv_actor_forward(sacv_handle h, const float* features, const float* frames_f32, int32_t n, const float* eps_dev_or_null,
+                       int32_t deterministic, float* pi, float* logp_or_null, uintptr_t stream);
+int sacv_critic_forward(sacv_handle h, int32_t which, const float* features, const float* frames_f32, const float* actions, int32_t n,
+                        float* q1, float* q2, uintptr_t stream);
+int sacv_debug_read(sacv_handle h, const char* name, float* dst_host, int64_t max_floats, int64_t* n_out);
+int64_t sacv_launch_count(sacv_handle h);
+
 #ifdef __cplusplus
 }
 #endif

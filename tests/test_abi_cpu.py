@@ -20,7 +20,7 @@ def lib():
 
 def test_header_symbols_all_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "sacb200.h")).read()
-    declared = set(re.findall(r"\b(sacb_[a-z_0-9]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(sac[bv]_[a-z_0-9]+)\s*\(", hdr))
     assert declared, "no declarations parsed"
     so = ctypes.CDLL(lib.LIB_PATH)
     for name in declared:

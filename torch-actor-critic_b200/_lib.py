@@ -32,6 +32,28 @@ class SacbLayout(C.Structure):
     ]
 
 
+class SacvConfig(C.Structure):
+    """sacv_config of include/sacb200.h (visual SAC engine)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32),
+        ("hidden1", C.c_int32), ("hidden2", C.c_int32), ("batch_size", C.c_int32),
+        ("vis_c", C.c_int32), ("vis_h", C.c_int32), ("vis_w", C.c_int32),
+        ("filters", C.c_int32 * 3), ("kernels", C.c_int32 * 3), ("strides", C.c_int32 * 3), ("dense", C.c_int32),
+        ("log_min_std", C.c_float), ("log_max_std", C.c_float), ("act_limit", C.c_float), ("precision", C.c_int32),
+        ("alpha", C.c_double), ("gamma", C.c_double), ("polyak", C.c_double), ("reward_scale", C.c_double),
+        ("lr_pi", C.c_double), ("lr_q", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double),
+        ("flags", C.c_uint32), ("reserved0", C.c_uint32), ("seed", C.c_uint64),
+    ]
+
+
+class SacvLayout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("actor_floats", "a_l0w", "a_l0b", "a_l1w", "a_l1b", "a_cnn", "a_muw", "a_lsw", "a_mub", "a_lsb",
+                                         "critic_floats", "critic_net_floats", "c_l0w", "c_l0b", "c_l1w", "c_l1b", "c_l2w", "c_l2b", "c_fw",
+                                         "c_fb", "c_cnn", "cnn_floats")] + [
+        ("cnn_w", C.c_int64 * 3), ("cnn_b", C.c_int64 * 3), ("cnn_lw", C.c_int64), ("cnn_lb", C.c_int64), ("cnn_fw", C.c_int64),
+        ("cnn_fb", C.c_int64), ("conv_h", C.c_int32 * 3), ("conv_w", C.c_int32 * 3), ("flat", C.c_int32), ("reserved0", C.c_int32)]
+
+
 class SacbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libsacb200 error {code}: {msg}")
@@ -74,6 +96,29 @@ _PROTOS = {
     "sacb_launch_count": (_I64, [_P]),
     "sacb_set_mode": (C.c_int, [_P, _I32]),
     "sacb_set_precision": (C.c_int, [_P, _I32]),
+    # ---- visual SAC engine (networks/convolutional.py + buffer/visual_replay_buffer.py path) ----
+    "sacv_last_error": (C.c_char_p, []),
+    "sacv_layout": (C.c_int, [C.POINTER(SacvConfig), C.POINTER(SacvLayout)]),
+    "sacv_create": (C.c_int, [C.POINTER(SacvConfig), C.POINTER(_P)]),
+    "sacv_destroy": (C.c_int, [_P]),
+    "sacv_bind_params": (C.c_int, [_P, _P, _P, _P]),
+    "sacv_bind_adam": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I64]),
+    "sacv_get_adam_steps": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
+    "sacv_set_scalar": (C.c_int, [_P, C.c_char_p, C.c_double]),
+    "sacv_bind_buffer": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64]),
+    "sacv_buffer_state": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "sacv_set_buffer_state": (C.c_int, [_P, _I64, _I64]),
+    "sacv_store": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _U]),
+    "sacv_sample": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U]),
+    "sacv_update": (C.c_int, [_P, _I32, _P, _P, _P, _P, _U]),
+    "sacv_load_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _U]),
+    "sacv_update_critic": (C.c_int, [_P, _P, _P, _U]),
+    "sacv_update_policy": (C.c_int, [_P, _P, _P, _U]),
+    "sacv_update_targets": (C.c_int, [_P, _U]),
+    "sacv_actor_forward": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _P, _P, _U]),
+    "sacv_critic_forward": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, _U]),
+    "sacv_debug_read": (C.c_int, [_P, C.c_char_p, _P, _I64, C.POINTER(_I64)]),
+    "sacv_launch_count": (_I64, [_P]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 
@@ -99,6 +144,13 @@ def load():
 def check(code):
     if code != 0:
         raise SacbError(code, load().sacb_last_error().decode())
+    return code
+
+
+def checkv(code):
+    """Status check for the sacv_* (visual engine) entry points."""
+    if code != 0:
+        raise SacbError(code, load().sacv_last_error().decode())
     return code
 
 

@@ -18,7 +18,10 @@ import torch.optim as optim
 
 from ..buffer.replay_buffer import Batch, ReplayBuffer
 from ..engine import ACTOR_PARAM_NAMES, CRITIC_PARAM_NAMES, Engine, actor_views, critic_views
+from ..buffer.visual_replay_buffer import VisualBatch, VisualReplayBuffer
+from ..networks.convolutional import VisualActor, VisualDoubleCritic
 from ..networks.linear import Actor, DoubleCritic
+from ..visual_engine import VisualEngine, actor_param_names, critic_param_names, vactor_views, vcritic_views
 from .mpi import num_procs, proc_id, setup_pytorch_for_mpi, sync_params
 
 logging.basicConfig(level=logging.INFO)
@@ -58,8 +61,23 @@ def _polyak_engine(source: DoubleCritic, target: DoubleCritic) -> Engine:
     return eng
 
 
+def _polyak_vengine(source: VisualDoubleCritic, target: VisualDoubleCritic) -> VisualEngine:
+    eng = getattr(target, "_polyak_engine", None)
+    if eng is None or eng._keep.get("critic") is not source.arena:
+        eng = VisualEngine(source.obs_dim, source.act_dim, source.vis_dim, source.hidden_sizes, batch_size=1, device=source._dev,
+                           **source._engine_kwargs())
+        eng.bind_params(critic=source.arena, target=target.arena)
+        object.__setattr__(target, "_polyak_engine", eng)
+    return eng
+
+
 def update_targets(source: nn.Module, target: nn.Module, polyak: float):
     """targ <- polyak*targ + (1-polyak)*src for every parameter (sac/algorithm.py:77-81), one fused kernel."""
+    if isinstance(source, VisualDoubleCritic) and isinstance(target, VisualDoubleCritic):
+        eng = _polyak_vengine(source, target)
+        eng.set_scalar("polyak", polyak)
+        eng.update_targets()
+        return
     if not (isinstance(source, DoubleCritic) and isinstance(target, DoubleCritic)):
         raise TypeError("update_targets expects arena-backed DoubleCritic modules")
     eng = _polyak_engine(source, target)
@@ -213,11 +231,75 @@ class SAC(object):
     def _entry(self, actor, critic, batch):
         return self._engines[(id(actor), id(critic), int(batch))]
 
+    # ---- visual path (networks/convolutional.py modules, buffer/visual_replay_buffer.py) --------------------------------
+    def _vengine(self, actor: VisualActor, critic: VisualDoubleCritic, batch: int, target=None, pi_opt=None, q_opt=None) -> VisualEngine:
+        if not isinstance(critic, VisualDoubleCritic):
+            raise TypeError("a VisualActor trains against a VisualDoubleCritic (main.py:69-87)")
+        key = (id(actor), id(critic), int(batch))
+        ent = self._engines.get(key)
+        if ent is None:
+            eng = VisualEngine(actor.obs_dim, actor.act_dim, actor.vis_dim, actor.hidden_sizes, batch_size=batch, device=actor._dev,
+                               alpha=self.alpha, gamma=self.gamma, polyak=self.polyak, reward_scale=self.reward_scale, seed=self.seed,
+                               **actor._engine_kwargs())
+            ent = dict(engine=eng, target=None, pi=None, q=None)
+            eng.bind_params(actor=actor.arena, critic=critic.arena, target=None)
+            self._engines[key] = ent
+        eng = ent["engine"]
+        for name, val in (("alpha", self.alpha), ("gamma", self.gamma), ("polyak", self.polyak), ("reward_scale", self.reward_scale)):
+            eng.set_scalar(name, val)
+        if target is not None and ent["target"] is not target:
+            eng.bind_params(actor=actor.arena, critic=critic.arena, target=target.arena)
+            ent["target"] = target
+        lay, dev = eng.layout, eng.tdev()
+        rebind = False
+        for which, opt, module in (("pi", pi_opt, actor), ("q", q_opt, critic)):
+            if opt is None:
+                continue
+            b = self._bindings.get(id(opt))
+            if b is None or b.opt is not opt or not b.still_bound():
+                _adam_hparams(opt)
+                if which == "pi":
+                    b = _AdamBinding(opt, module, actor_param_names(),
+                                     lambda a: vactor_views(lay, a, actor.obs_dim, actor.act_dim, actor.vis_dim[0], actor.hidden_sizes,
+                                                            actor.filters, actor.kernel_sizes), lay.actor_floats, dev)
+                else:
+                    b = _AdamBinding(opt, module, critic_param_names(),
+                                     lambda a: vcritic_views(lay, a, critic.obs_dim, critic.act_dim, critic.vis_dim[0], critic.hidden_sizes,
+                                                             critic.filters, critic.kernel_sizes), lay.critic_floats, dev)
+                self._bindings[id(opt)] = b
+            if ent[which] is not b:
+                ent[which], rebind = b, True
+        if not rebind and (ent["pi"] is not None or ent["q"] is not None):
+            sa, sc = eng.adam_steps()
+            rebind = (ent["pi"] is not None and ent["pi"].steps != sa) or (ent["q"] is not None and ent["q"].steps != sc)
+        if rebind:
+            pi, q = ent["pi"], ent["q"]
+            eng.bind_adam(pi.m if pi else None, pi.v if pi else None, pi.steps if pi else 0, q.m if q else None, q.v if q else None,
+                          q.steps if q else 0)
+        for b, which in ((ent["pi"], "pi"), (ent["q"], "q")):
+            if b is not None:
+                lr, b1, b2, eps = _adam_hparams(b.opt)
+                eng.set_scalar(f"lr_{which}", lr)
+                eng.set_scalar("beta1", b1); eng.set_scalar("beta2", b2); eng.set_scalar("adam_eps", eps)
+        return eng
+
+    @staticmethod
+    def _load_visual(eng: VisualEngine, samples: VisualBatch):
+        eng.load_batch(samples.states.features, samples.states.frame, samples.actions, samples.rewards, samples.next_states.features,
+                       samples.next_states.frame, samples.done)
+
     # ------------------------------------------------------------------------------------------------------------
     def update_critic(self, q_opt: optim.Optimizer, actor: nn.Module, critic: nn.Module, target_critic: nn.Module,
                       samples: Batch, eps=None) -> torch.Tensor:
         """One critic step on `samples` (sac/algorithm.py:115-141): soft Bellman target, twin MSE, hand-derived
         backward, (multi-GPU: NCCL gradient average,) Adam.  Returns loss_q as a 0-dim CUDA tensor."""
+        if isinstance(actor, VisualActor):                              # VisualBatch (visual_replay_buffer.py:12-18)
+            B = samples.actions.shape[0]
+            eng = self._vengine(actor, critic, B, target=target_critic, q_opt=q_opt)
+            self._load_visual(eng, samples)
+            loss_q = eng.update_critic(eps)
+            self._entry(actor, critic, B)["q"].advance(1)
+            return loss_q
         B = samples.states.shape[0]
         eng = self._engine(actor, critic, B, target=target_critic, q_opt=q_opt)
         eng.load_batch(samples.states, samples.actions, samples.rewards, samples.next_states, samples.done)
@@ -227,6 +309,13 @@ class SAC(object):
 
     def update_policy(self, pi_opt: optim.Optimizer, actor: nn.Module, critic: nn.Module, samples: Batch, eps=None) -> torch.Tensor:
         """One actor step on `samples` (sac/algorithm.py:143-162); the critic is only read."""
+        if isinstance(actor, VisualActor):
+            B = samples.actions.shape[0]
+            eng = self._vengine(actor, critic, B, pi_opt=pi_opt)
+            self._load_visual(eng, samples)
+            loss_pi = eng.update_policy(eps)
+            self._entry(actor, critic, B)["pi"].advance(1)
+            return loss_pi
         B = samples.states.shape[0]
         eng = self._engine(actor, critic, B, pi_opt=pi_opt)
         eng.load_batch(samples.states, samples.actions, samples.rewards, samples.next_states, samples.done)
@@ -237,6 +326,23 @@ class SAC(object):
     def update_burst(self, n_updates, actor, critic, target_critic, buffer: ReplayBuffer, pi_opt, q_opt, idx=None, eps=None):
         """`n_updates` x (sample, update_critic, update_policy, update_targets) = the inner loop
         sac/algorithm.py:274-278, as one persistent-kernel launch.  Returns (loss_q[n], loss_pi[n]) device tensors."""
+        if isinstance(actor, VisualActor):
+            if not isinstance(buffer, VisualReplayBuffer):
+                raise TypeError("a visual update_burst needs the HBM VisualReplayBuffer of this package")
+            eng = self._vengine(actor, critic, self.batch_size, target=target_critic, pi_opt=pi_opt, q_opt=q_opt)
+            buffer.flush()
+            ent = self._entry(actor, critic, self.batch_size)
+            if ent.get("buffer") is not buffer:
+                eng.bind_buffer(buffer._features, buffer._frames, buffer._actions, buffer._rewards, buffer._next_features, buffer._next_frames,
+                                buffer._done)
+                ent["buffer"] = buffer
+            if buffer.size < self.batch_size:
+                raise ValueError("Sample larger than population or is negative")
+            eng.set_buffer_state(buffer.ptr, buffer.size)
+            lq, lp = eng.update(n_updates, idx=idx, eps=eps)
+            ent["pi"].advance(n_updates)
+            ent["q"].advance(n_updates)
+            return lq, lp
         if not isinstance(buffer, ReplayBuffer):
             raise TypeError("update_burst needs the HBM ReplayBuffer of this package")
         eng = self._engine(actor, critic, self.batch_size, target=target_critic, pi_opt=pi_opt, q_opt=q_opt)
