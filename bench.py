@@ -401,6 +401,11 @@ def run_gpu(args):
             del rig2
         except Exception as ex:                                       # never lose the C1 line to the side measurement
             line["config"]["extra_workloads"] = {"c2": {"error": f"{type(ex).__name__}: {ex}"}}
+    if world == 1 and wl.name == "c1" and not args.no_extra:
+        try:
+            line["config"]["extra_workloads"]["c5"] = run_visual_extra(local, pk, args)
+        except Exception as ex:
+            line["config"].setdefault("extra_workloads", {})["c5"] = {"error": f"{type(ex).__name__}: {ex}"}
     if world == 1 and not args.no_cpu:
         arrays = wl.synth(0)
         rate, done, kind, probe, cores = cpu_arm(wl, arrays, 300, 20, budget_s=25.0, probe_threads=())
@@ -408,6 +413,70 @@ def run_gpu(args):
                                 "sample": f"{done} updates of the {'unmodified reference (oracle/_ref)' if kind == 'reference' else 'torch-CPU port'} "
                                           f"at {REF_THREADS} torch threads (main.py:130) on the same synthetic arrays; host cpu_count={cores}"}
     print(json.dumps(line), flush=True)
+
+
+def run_visual_extra(local, pk, args):
+    """BASELINE configs[4]: visual SAC (buffer/visual_replay_buffer.py + networks/convolutional.py), 84x84x3 frames, batch 256,
+    features 168 / actions 56 (environments/wall_runner.py:20-21), through the public API: VisualReplayBuffer (uint8 HBM
+    ring) -> SAC.update_burst."""
+    import torch
+    import torch.optim as optim
+    from copy import deepcopy
+    from torch_actor_critic_b200.buffer.visual_replay_buffer import VisualReplayBuffer
+    from torch_actor_critic_b200.networks.convolutional import VisualActor, VisualDoubleCritic
+    from torch_actor_critic_b200.sac.algorithm import SAC
+    O, A, V, H, B, N = 168, 56, (3, 84, 84), [256, 256], 256, 8192
+    label = "visual SAC: 3x84x84 uint8 frames, features 168, actions 56, conv 32/64/64 (k8s4,k4s2,k3s1) + 512 dense, MLP 256x256, batch=256"
+    rng = np.random.default_rng(5)
+    arr = dict(features=rng.standard_normal((N, O), dtype=np.float32), frames=rng.integers(0, 256, (N, *V), dtype=np.uint8),
+               actions=rng.uniform(-1, 1, (N, A)).astype(np.float32), rewards=rng.standard_normal(N, dtype=np.float32),
+               next_features=rng.standard_normal((N, O), dtype=np.float32), next_frames=rng.integers(0, 256, (N, *V), dtype=np.uint8),
+               done=rng.random(N) < 1e-3)
+    torch.manual_seed(0)
+    actor = VisualActor(O, A, V, H, 1.0, device=local)
+    critic = VisualDoubleCritic(O, A, V, H, device=local)
+    with torch.no_grad():                                            # raw 0..255 pixels: scale the first conv like the fixtures do
+        for m in (actor.visual_network, critic.q1.visual_network, critic.q2.visual_network):
+            m.conv_0.weight.div_(64.0)
+    target = deepcopy(critic)
+    pi_opt, q_opt = optim.Adam(actor.parameters(), lr=3e-4), optim.Adam(critic.parameters(), lr=3e-4)
+    sac = SAC(alpha=0.2, gamma=0.99, polyak=0.995, reward_scale=1.0, epochs=1, batch_size=B, start_steps=0, steps_per_epoch=1,
+              max_ep_len=1000, update_after=0, update_every=UPDATE_EVERY, save_every=1)
+    buf = VisualReplayBuffer(N, A, obs_dim=O, vis_dim=V, device=local)
+    buf.store_many(arr["features"], arr["frames"], arr["actions"], arr["rewards"], arr["next_features"], arr["next_frames"], arr["done"])
+    torch.cuda.synchronize()
+    steps, warm = 30, 5
+    sac.update_burst(warm, actor, critic, target, buf, pi_opt, q_opt)
+    torch.cuda.synchronize()
+    sam = ClockSampler(local); sam.start()
+    ms_all = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); lq, lp = sac.update_burst(steps, actor, critic, target, buf, pi_opt, q_opt); e1.record()
+        torch.cuda.synchronize()
+        ms_all.append(e0.elapsed_time(e1))
+    clocks = sam.stop()
+    ms = float(np.median(ms_all))
+    flops = 2 * B * 8_520_000 * 14                                   # SURVEY.md section 8d: 8 CNN forward + 3 backward (~2x) passes
+    eng = sac._entry(actor, critic, B)["engine"]
+    tf = flops * steps / (ms * 1e-3) / 1e12
+    out = {"workload": label, "value": round(steps / (ms * 1e-3), 2), "unit": UNIT, "steps": steps, "warmup": warm,
+           "ms_per_step": round(ms / steps, 4), "dtype": "f32", "gemm_arithmetic": "tensor-core 3xTF32 via mma.sync (fp32-level accuracy)",
+           "finite_losses": bool(torch.isfinite(lq).all() and torch.isfinite(lp).all()),
+           "gpu_launches_per_update": int(eng.launch_count() // (warm + 3 * steps)),
+           "roofline": {"bound": "tensor", "achieved": round(tf, 2), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                        "frac": round(tf / pk["tensor_sustained"], 5), "peak_source": pk["src"] + " bf16_tflops_sustained",
+                        "flops_per_update": flops, "note": "fp32-level arithmetic (3 TF32 MMAs per product) against the bf16 dense peak"},
+           "clocks": clocks}
+    if not args.no_cpu:
+        from oracle import build_ref
+        if build_ref.available():
+            from oracle.ref_runner import reference_visual_rate
+            sub = {k: v[:512] for k, v in arr.items()}
+            rate, done = reference_visual_rate(sub, O, A, V, H, B, 1.0, REF_THREADS, 3, 1, 25.0)
+            out["cpu_baseline"] = {"value": round(rate, 3), "unit": UNIT, "cores": REF_THREADS, "kind": "reference",
+                                   "sample": f"{done} updates of the unmodified reference visual loop (oracle/_ref) at {REF_THREADS} torch threads, 512-transition buffer"}
+    return out
 
 
 def main():

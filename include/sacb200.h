@@ -114,6 +114,11 @@ int sacb_bind_buffer(sacb_handle h, float* state_dev, float* actions_dev, float*
 int sacb_store(sacb_handle h, const float* obs_host, const float* act_host, const float* rew_host,
                const float* next_obs_host, const uint8_t* done_host, int64_t count, uintptr_t stream);
 /* Ring state (ReplayBuffer.ptr / .size / .max_size). */
+/* The same ring as ONE packed array [capacity][pitch] of float32 records  [ state(O) | action(A) | reward | next_state(O) |
+ * done (0/1) | pad ]  with a 16-byte-aligned pitch (the Python ReplayBuffer uses a multiple of 64 bytes).  A sampled row is
+ * then one aligned, contiguous read -- fetched inside the update kernel by one TMA bulk copy (cp.async.bulk) per row into
+ * shared memory -- instead of five unaligned ones, and sacb_store ships rows with one H2D copy per ring segment. */
+int sacb_bind_buffer_packed(sacb_handle h, float* records_dev, int32_t pitch_floats, int64_t capacity);
 int sacb_buffer_state(sacb_handle h, int64_t* ptr, int64_t* size, int64_t* capacity);
 int sacb_set_buffer_state(sacb_handle h, int64_t ptr, int64_t size);
 

@@ -67,3 +67,48 @@ def reference_rate(arrays, obs_dim, act_dim, hidden, batch, act_limit, threads, 
     loop = ReferenceLoop(arrays, obs_dim, act_dim, hidden, batch, act_limit, threads)
     dt, done = loop.time_updates(n_updates, warmup, max_seconds)
     return done / dt, done
+
+
+def reference_visual_rate(arrays, obs_dim, act_dim, vis_dim, hidden, batch, act_limit, threads, n_updates, warmup, max_seconds):
+    """updates/s of the UNMODIFIED reference's visual hot loop (VisualReplayBuffer.sample -> SAC.update_critic ->
+    SAC.update_policy -> update_targets with VisualActor / VisualDoubleCritic, main.py:63-87) on the host."""
+    import torch
+    from copy import deepcopy
+    from .ref_stubs import import_reference_visual
+    (alg, VisualBatch, VisualReplayBuffer, MultiObservation, VisualActor, VisualCritic, VisualDoubleCritic, _cs, _cnn) = import_reference_visual(REF_ROOT)
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    actor = VisualActor(obs_dim, act_dim, tuple(vis_dim), list(hidden), act_limit)
+    critic = VisualDoubleCritic(obs_dim, act_dim, tuple(vis_dim), list(hidden))
+    target = deepcopy(critic)
+    for p in target.parameters():
+        p.requires_grad = False
+    pi_opt = torch.optim.Adam(actor.parameters(), lr=3e-4)
+    q_opt = torch.optim.Adam(critic.parameters(), lr=3e-4)
+    sac = alg.SAC(alpha=0.2, gamma=0.99, polyak=0.995, reward_scale=1.0, epochs=1, batch_size=batch, start_steps=0, steps_per_epoch=1,
+                  max_ep_len=1000, update_after=0, update_every=50, save_every=1)
+    torch.set_num_threads(threads)
+    n = len(arrays["rewards"])
+    buf = VisualReplayBuffer(n, act_dim)
+    for i in range(n):
+        obs = MultiObservation(torch.FloatTensor(arrays["features"][i]), torch.FloatTensor(arrays["frames"][i].astype(np.float32)))
+        nobs = MultiObservation(torch.FloatTensor(arrays["next_features"][i]), torch.FloatTensor(arrays["next_frames"][i].astype(np.float32)))
+        buf.store(obs, arrays["actions"][i], arrays["rewards"][i], nobs, arrays["done"][i])
+
+    def one():
+        b = buf.sample(batch)
+        lq = sac.update_critic(q_opt, actor, critic, target, b)
+        lp = sac.update_policy(pi_opt, actor, critic, b)
+        alg.update_targets(critic, target, sac.polyak)
+        lp.cpu().detach().numpy(); lq.cpu().detach().numpy()
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    done = 0
+    while done < n_updates:
+        one()
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    return done / (time.perf_counter() - t0), done

@@ -74,6 +74,7 @@ _PROTOS = {
     "sacb_get_adam_steps": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
     "sacb_set_scalar": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "sacb_bind_buffer": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64]),
+    "sacb_bind_buffer_packed": (C.c_int, [_P, _P, _I32, _I64]),
     "sacb_store": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _U]),
     "sacb_buffer_state": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "sacb_set_buffer_state": (C.c_int, [_P, _I64, _I64]),

@@ -1,9 +1,11 @@
 """HBM-resident replay ring with the reference's ReplayBuffer / Batch surface (buffer/replay_buffer.py:8-54).
 
-The five arrays are struct-of-arrays torch CUDA tensors (`state[N,O]`, `actions[N,A]`, `rewards[N]`,
-`next_state[N,O]` float32, `done[N]` bool) that the CUDA engine gathers from directly.  `store` stages rows in
-host memory and flushes them with one H2D copy per array (`sacb_store`); `sample` draws a duplicate-free index set
-on the device (cuRAND Philox) and gathers with a CUDA kernel (`sacb_sample`).
+The ring is ONE packed torch CUDA tensor `[N, pitch]` of float32 records `[state(O) | action(A) | reward | next_state(O) |
+done | pad]`, pitch a multiple of 64 bytes, so that a sampled transition is a single aligned, contiguous read (inside the
+update kernel: one TMA bulk copy per row); `state`, `actions`, `rewards`, `next_state`, `done` -- the reference's five
+attributes -- are strided views of it.  `store` stages rows in host memory and flushes them with one H2D copy per ring
+segment (`sacb_store`); `sample` draws a duplicate-free index set on the device (cuRAND Philox) and gathers with a CUDA
+kernel (`sacb_sample`).
 """
 from __future__ import annotations
 
@@ -37,12 +39,13 @@ class ReplayBuffer:
         self._engine = Engine(obs_dim, act_dim, [4, 4], batch_size=256, max_burst=1, device=self._dev, seed=seed)
         d = self._engine.tdev()
         self.obs_dim, self.act_dim = obs_dim, act_dim
-        self._state = torch.zeros(size, obs_dim, dtype=torch.float32, device=d)
-        self._actions = torch.zeros(size, act_dim, dtype=torch.float32, device=d)
-        self._rewards = torch.zeros(size, dtype=torch.float32, device=d)
-        self._next_state = torch.zeros(size, obs_dim, dtype=torch.float32, device=d)
-        self._done = torch.zeros(size, dtype=torch.bool, device=d)
-        self._engine.bind_buffer(self._state, self._actions, self._rewards, self._next_state, self._done)
+        O, A = obs_dim, act_dim
+        self.pitch = (2 * O + A + 2 + 15) // 16 * 16                    # floats; records start on 64-byte boundaries
+        self._rec = torch.zeros(size, self.pitch, dtype=torch.float32, device=d)
+        self._state, self._actions = self._rec[:, :O], self._rec[:, O:O + A]
+        self._rewards, self._next_state = self._rec[:, O + A], self._rec[:, O + A + 1:2 * O + A + 1]
+        self._done_f = self._rec[:, 2 * O + A + 1]
+        self._engine.bind_buffer_packed(self._rec)
         self.max_size = size
         # host staging (flushed lazily: before any sample/update/array access)
         n = min(self._STAGE_ROWS, size)
@@ -79,7 +82,7 @@ class ReplayBuffer:
     actions = property(lambda self: (self.flush(), self._actions)[1])
     rewards = property(lambda self: (self.flush(), self._rewards)[1])
     next_state = property(lambda self: (self.flush(), self._next_state)[1])
-    done = property(lambda self: (self.flush(), self._done)[1])
+    done = property(lambda self: (self.flush(), self._done_f != 0)[1])
 
     def store(self, obs, act, rew, next_obs, done):
         """One transition at `ptr`; ptr wraps, size saturates (buffer/replay_buffer.py:29-43)."""

@@ -106,6 +106,7 @@ struct sacb_engine {
     long long exch_pi = 0, exch_q = 0;          // gradient exchanges done so far (peer-flag epochs): never reset by a re-bind
     float *bs = nullptr, *ba = nullptr, *br = nullptr, *bs2 = nullptr;
     uint8_t* bd = nullptr;
+    float* brec = nullptr; int rec_pitch = 0;   // packed ring (sacb_bind_buffer_packed): [s | a | r | s' | d | pad] per transition
     long long cap = 0, ptr = 0, size = 0;
     // workspace
     float* ws = nullptr;
@@ -280,6 +281,25 @@ __global__ void sample_gather_kernel(const long long* __restrict__ idx, int B, i
     if (lane == 0) { r[m] = br[row]; d[m] = bd[row] ? 1.f : 0.f; if (idx_out) idx_out[m] = row; }
 }
 
+// same from the packed ring: one record per row, 128-bit loads
+__global__ void sample_gather_packed_kernel(const long long* __restrict__ idx, int B, int O, int A, const float* __restrict__ rec, int pitch,
+                                            float* s, float* a, float* r, float* s2, float* d, long long* idx_out) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= B) return;
+    const long long row = idx[m];
+    const float* src = rec + (size_t)row * pitch;
+    const int W = 2 * O + A + 2;
+    for (int c = lane; c < W; c += 32) {
+        const float v = src[c];
+        if (c < O) s[(size_t)m * O + c] = v;
+        else if (c < O + A) a[(size_t)m * A + c - O] = v;
+        else if (c == O + A) r[m] = v;
+        else if (c < 2 * O + A + 1) s2[(size_t)m * O + c - (O + A + 1)] = v;
+        else d[m] = v != 0.f ? 1.f : 0.f;
+    }
+    if (lane == 0 && idx_out) idx_out[m] = row;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------------------
@@ -289,6 +309,7 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
     ra.jobs = e->d_jobs; ra.phases = e->d_phases;
     ra.barrier = e->barrier;
     ra.buf_state = e->bs; ra.buf_actions = e->ba; ra.buf_rewards = e->br; ra.buf_next_state = e->bs2; ra.buf_done = e->bd;
+    ra.buf_rec = e->brec; ra.rec_pitch = e->rec_pitch;
     ra.alpha = (float)c.alpha; ra.gamma = (float)c.gamma; ra.polyak = (float)c.polyak; ra.reward_scale = (float)c.reward_scale;
     ra.polyak_c = (float)(1.0 - c.polyak);          // `(1 - polyak) * src` with a python-float polyak (sac/algorithm.py:81)
     ra.log_min_std = c.log_min_std; ra.log_max_std = c.log_max_std; ra.act_limit = c.act_limit;
@@ -522,6 +543,19 @@ int sacb_bind_buffer(sacb_handle e, float* s, float* a, float* r, float* s2, uin
     if (!e) return fail(SACB_ERR_INVALID, "null handle");
     if (!s || !a || !r || !s2 || !d || cap < 1) return fail(SACB_ERR_INVALID, "bad buffer arrays");
     e->bs = s; e->ba = a; e->br = r; e->bs2 = s2; e->bd = d; e->cap = cap;
+    e->brec = nullptr; e->rec_pitch = 0;
+    if (e->ptr >= cap) e->ptr = 0;
+    if (e->size > cap) e->size = cap;
+    return 0;
+}
+
+int sacb_bind_buffer_packed(sacb_handle e, float* rec, int32_t pitch_floats, int64_t cap) {
+    if (!e) return fail(SACB_ERR_INVALID, "null handle");
+    const int W = 2 * e->cfg.obs_dim + e->cfg.act_dim + 2;
+    if (!rec || cap < 1 || pitch_floats < W || (pitch_floats & 3) || ((uintptr_t)rec & 15))
+        return fail(SACB_ERR_INVALID, "packed ring: need a 16-byte-aligned array with a pitch that is a multiple of 4 floats and >= %d", W);
+    e->brec = rec; e->rec_pitch = pitch_floats; e->cap = cap;
+    e->bs = rec; e->ba = rec; e->br = rec; e->bs2 = rec; e->bd = (uint8_t*)rec;      // "bound" markers for the SoA checks
     if (e->ptr >= cap) e->ptr = 0;
     if (e->size > cap) e->size = cap;
     return 0;
@@ -550,6 +584,40 @@ int sacb_store(sacb_handle e, const float* obs, const float* act, const float* r
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(e->cfg.device));
     const size_t O = e->cfg.obs_dim, A = e->cfg.act_dim;
+    if (e->brec) {
+        // packed ring: rows are assembled as records in pinned staging and go to HBM with ONE copy per contiguous ring segment
+        const size_t P = (size_t)e->rec_pitch;
+        const int64_t chunk = 4096;
+        if (!e->stage || e->stage_bytes < (size_t)chunk * P * sizeof(float)) {
+            if (e->stage) { CU(cudaEventSynchronize(e->stage_ev)); CU(cudaFreeHost(e->stage)); e->stage = nullptr; }
+            e->stage_bytes = (size_t)chunk * P * sizeof(float);
+            CU(cudaMallocHost(&e->stage, e->stage_bytes));
+        }
+        int64_t done_rows = 0;
+        while (done_rows < count) {
+            int64_t n = count - done_rows;
+            if (n > chunk) n = chunk;
+            if (n > e->cap - e->ptr) n = e->cap - e->ptr;
+            CU(cudaEventSynchronize(e->stage_ev));
+            float* rec = (float*)e->stage;
+            for (int64_t i = 0; i < n; ++i) {
+                float* r = rec + i * P;
+                const int64_t g = done_rows + i;
+                memcpy(r, obs + g * O, O * sizeof(float));
+                memcpy(r + O, act + g * A, A * sizeof(float));
+                r[O + A] = rew[g];
+                memcpy(r + O + A + 1, nobs + g * O, O * sizeof(float));
+                r[2 * O + A + 1] = done[g] ? 1.f : 0.f;
+                for (size_t c = 2 * O + A + 2; c < P; ++c) r[c] = 0.f;
+            }
+            CU(cudaMemcpyAsync(e->brec + e->ptr * P, rec, (size_t)n * P * sizeof(float), cudaMemcpyHostToDevice, st));
+            CU(cudaEventRecord(e->stage_ev, st));
+            e->ptr = (e->ptr + n) % e->cap;                                   // buffer/replay_buffer.py:42
+            e->size = e->size + n > e->cap ? e->cap : e->size + n;            // :43
+            done_rows += n;
+        }
+        return 0;
+    }
     const size_t row_bytes = (2 * O + A + 1) * sizeof(float) + 1;
     const int64_t chunk_rows = 4096;
     if (!e->stage) {
@@ -635,8 +703,12 @@ int sacb_sample(sacb_handle e, int32_t batch, const int64_t* idx_in, float* s, f
             idx = e->idx_buf;
         }
     }
-    sample_gather_kernel<<<(batch + 7) / 8, 256, 0, st>>>(idx, batch, e->cfg.obs_dim, e->cfg.act_dim, e->bs, e->ba, e->br, e->bs2,
-                                                          e->bd, s, a, r, s2, d, (long long*)idx_out);
+    if (e->brec)
+        sample_gather_packed_kernel<<<(batch + 7) / 8, 256, 0, st>>>(idx, batch, e->cfg.obs_dim, e->cfg.act_dim, e->brec, e->rec_pitch, s, a, r, s2, d,
+                                                                     (long long*)idx_out);
+    else
+        sample_gather_kernel<<<(batch + 7) / 8, 256, 0, st>>>(idx, batch, e->cfg.obs_dim, e->cfg.act_dim, e->bs, e->ba, e->br, e->bs2,
+                                                              e->bd, s, a, r, s2, d, (long long*)idx_out);
     CU(cudaGetLastError());
     e->launches++;
     if (tmp) CU(cudaFreeAsync(tmp, st));

@@ -180,6 +180,12 @@ class Engine:
         check(self._lib.sacb_bind_buffer(self._h, _ptr(state), _ptr(actions), _ptr(rewards), _ptr(next_state), _ptr(done), cap))
         self._keep.update(buf=(state, actions, rewards, next_state, done))
 
+    def bind_buffer_packed(self, records):
+        """Packed ring [N, pitch] float32: [state | action | reward | next_state | done | pad] per row (include/sacb200.h)."""
+        _check_tensor(records, "records", device=self.device)
+        check(self._lib.sacb_bind_buffer_packed(self._h, _ptr(records), int(records.shape[1]), int(records.shape[0])))
+        self._keep.update(buf=(records,))
+
     def buffer_state(self):
         p, s, c = C.c_int64(), C.c_int64(), C.c_int64()
         check(self._lib.sacb_buffer_state(self._h, C.byref(p), C.byref(s), C.byref(c)))

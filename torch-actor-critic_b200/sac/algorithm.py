@@ -349,7 +349,7 @@ class SAC(object):
         buffer.flush()
         ent = self._entry(actor, critic, self.batch_size)
         if ent.get("buffer") is not buffer:
-            eng.bind_buffer(buffer._state, buffer._actions, buffer._rewards, buffer._next_state, buffer._done)
+            eng.bind_buffer_packed(buffer._rec)
             ent["buffer"] = buffer
         if buffer.size < self.batch_size:
             raise ValueError("Sample larger than population or is negative")
