@@ -1,0 +1,15 @@
+python tools/visual_bench.py 10 1
+python tools/visual_bench.py 10 0
+ncu --metrics gpu__time_duration.sum --clock-control none -s 450 -c 160 --csv --log-file gpurun_out/r2_visual_launches.csv python tools/visual_bench.py 2 1 > /dev/null 2>&1
+python - <<PY
+import csv, collections
+rows=[r for r in csv.reader(open("gpurun_out/r2_visual_launches.csv")) if len(r)>5 and r[0].isdigit()]
+hdr=None
+agg=collections.defaultdict(lambda:[0,0.0])
+for r in rows:
+    name=r[4]; val=float(r[-1].replace(",",""))
+    agg[name][0]+=1; agg[name][1]+=val
+tot=sum(v[1] for v in agg.values())
+for k,v in sorted(agg.items(), key=lambda x:-x[1][1])[:14]: print(f"{v[1]/1e3:9.1f} us {v[0]:4d}x {100*v[1]/tot:5.1f}%  {k[:90]}")
+print("total us", tot/1e3)
+PY
