@@ -380,7 +380,7 @@ static void build_programs(sacb_engine* e) {
                 }
                 return j; };
             auto st = [](Job j) { j.b_static = 1; return j; };
-            const int cw = 256;                                        // columns per tile of the partial-sum reductions
+            const int cw = 512;                                        // columns per tile of the partial-sum reductions
 
             e->p_fold.begin = (int)e->phases.size();
             { int p0 = b.phase(); e->phases[p0].pad = 1; b.add(gather_f(0, 1)); }

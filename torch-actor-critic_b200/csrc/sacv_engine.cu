@@ -175,6 +175,9 @@ static int gemm(sacv_engine* e, cudaStream_t st, bool ak, bool bk, const float* 
     return 0;
 }
 
+// column sums of X [M, N] (pitch ld) for nz batched matrices; tall matrices go through per-row-block partials (fixed order)
+static int colsum(sacv_engine* e, cudaStream_t st, const float* X, float* out, int M, int N, int ld, long long sX, long long sOut, int nz);
+
 static inline unsigned nblk(long long n, int per = 256) { long long b = (n + per - 1) / per; return (unsigned)(b > 65535LL * 16 ? 65535LL * 16 : b); }
 #define KCHK() do { CUV(cudaGetLastError()); e->launches++; } while (0)
 
@@ -220,8 +223,7 @@ static int cnn_backward(sacv_engine* e, cudaStream_t st, const float* P, float* 
     KCHK();
     // linear: d = a3n . Wl^T + bl
     if (int r = gemm(e, st, false, false, e->dd, D, (long long)B * D, b.a3n, L.flat, (long long)B * L.flat, G + L.cnn_lw, L.flat, sP, nullptr, 0, D, L.flat, B, EPI_NONE, nz)) return r;
-    colsum_kernel<<<dim3((D + 31) / 32, 1, nz), 256, 0, st>>>(e->dd, G + L.cnn_lb, B, D, D, (long long)B * D, sP);
-    KCHK();
+    if (int r = colsum(e, st, e->dd, G + L.cnn_lb, B, D, D, (long long)B * D, sP, nz)) return r;
     if (int r = gemm(e, st, true, false, e->dd, D, (long long)B * D, P + L.cnn_lw, L.flat, sP, e->da3n, L.flat, (long long)B * L.flat, nullptr, 0, B, L.flat, D, EPI_NONE, nz)) return r;
     for (int z = 0; z < nz; ++z) {
         permute_flat_kernel<<<nblk(M3 * F2), 256, 0, st>>>(e->da3n + (long long)z * B * L.flat, b.a3 + z * M3 * F2, e->da3 + z * M3 * F2, B, e->P[2], F2, 1);
@@ -229,8 +231,7 @@ static int cnn_backward(sacv_engine* e, cudaStream_t st, const float* P, float* 
     }
     // conv 2
     if (int r = gemm(e, st, false, false, e->da3, F2, M3 * F2, b.col3, e->K[2], M3 * e->K[2], G + L.cnn_w[2], e->K[2], sP, nullptr, 0, F2, e->K[2], (int)M3, EPI_NONE, nz)) return r;
-    colsum_kernel<<<dim3((F2 + 31) / 32, 1, nz), 256, 0, st>>>(e->da3, G + L.cnn_b[2], (int)M3, F2, F2, M3 * F2, sP);
-    KCHK();
+    if (int r = colsum(e, st, e->da3, G + L.cnn_b[2], (int)M3, F2, F2, M3 * F2, sP, nz)) return r;
     if (int r = gemm(e, st, true, false, e->da3, F2, M3 * F2, P + L.cnn_w[2], e->K[2], sP, e->dcol3, e->K[2], M3 * e->K[2], nullptr, 0, (int)M3, e->K[2], F2, EPI_NONE, nz)) return r;
     for (int z = 0; z < nz; ++z) {
         col2im_mask_kernel<<<nblk(M2 * F1), 256, 0, st>>>(e->dcol3 + z * M3 * e->K[2], b.a2 + z * M2 * F1, e->da2 + z * M2 * F1, B, F1, L.conv_h[1], L.conv_w[1], c.kernels[2], c.strides[2], L.conv_h[2], L.conv_w[2]);
@@ -238,8 +239,7 @@ static int cnn_backward(sacv_engine* e, cudaStream_t st, const float* P, float* 
     }
     // conv 1
     if (int r = gemm(e, st, false, false, e->da2, F1, M2 * F1, b.col2, e->K[1], M2 * e->K[1], G + L.cnn_w[1], e->K[1], sP, nullptr, 0, F1, e->K[1], (int)M2, EPI_NONE, nz)) return r;
-    colsum_kernel<<<dim3((F1 + 31) / 32, 1, nz), 256, 0, st>>>(e->da2, G + L.cnn_b[1], (int)M2, F1, F1, M2 * F1, sP);
-    KCHK();
+    if (int r = colsum(e, st, e->da2, G + L.cnn_b[1], (int)M2, F1, F1, M2 * F1, sP, nz)) return r;
     if (int r = gemm(e, st, true, false, e->da2, F1, M2 * F1, P + L.cnn_w[1], e->K[1], sP, e->dcol2, e->K[1], M2 * e->K[1], nullptr, 0, (int)M2, e->K[1], F1, EPI_NONE, nz)) return r;
     for (int z = 0; z < nz; ++z) {
         col2im_mask_kernel<<<nblk(M1 * F0), 256, 0, st>>>(e->dcol2 + z * M2 * e->K[1], b.a1 + z * M1 * F0, e->da1 + z * M1 * F0, B, F0, L.conv_h[0], L.conv_w[0], c.kernels[1], c.strides[1], L.conv_h[1], L.conv_w[1]);
@@ -247,7 +247,24 @@ static int cnn_backward(sacv_engine* e, cudaStream_t st, const float* P, float* 
     }
     // conv 0 (no input gradient: the frames are data)
     if (int r = gemm(e, st, false, false, e->da1, F0, M1 * F0, col1, e->K[0], 0, G + L.cnn_w[0], e->K[0], sP, nullptr, 0, F0, e->K[0], (int)M1, EPI_NONE, nz)) return r;
-    colsum_kernel<<<dim3((F0 + 31) / 32, 1, nz), 256, 0, st>>>(e->da1, G + L.cnn_b[0], (int)M1, F0, F0, M1 * F0, sP);
+    if (int r = colsum(e, st, e->da1, G + L.cnn_b[0], (int)M1, F0, F0, M1 * F0, sP, nz)) return r;
+    return 0;
+}
+
+static int colsum(sacv_engine* e, cudaStream_t st, const float* X, float* out, int M, int N, int ld, long long sX, long long sOut, int nz) {
+    const int cb = (N + 31) / 32;
+    if (M <= 4096) {
+        colsum_kernel<<<dim3(cb, 1, nz), 256, 0, st>>>(X, out, M, N, ld, sX, sOut);
+        KCHK();
+        return 0;
+    }
+    int S = (M + 1023) / 1024;
+    if (S > 128) S = 128;
+    const int rpb = (M + S - 1) / S;
+    // partials [nz][S][N] live in the split-K scratch (a GEMM never runs concurrently on this stream)
+    colsum_kernel<<<dim3(cb, S, nz), 256, 0, st>>>(X, e->partial, M, N, ld, sX, (long long)S * N, rpb, N);
+    KCHK();
+    colsum_kernel<<<dim3(cb, 1, nz), 256, 0, st>>>(e->partial, out, S, N, N, (long long)S * N, sOut);
     KCHK();
     return 0;
 }
@@ -335,7 +352,7 @@ static int critic_step(sacv_engine* e, cudaStream_t st, float* loss_out, bool po
     if (int r = critic_mlp_forward(e, st, e->pc, e->xs, e->cq.c, e->ch1, e->ch2, e->cm, e->qv)) return r;
     critic_loss_rows_kernel<<<(B + 127) / 128, 128, 0, st>>>(e->qv, e->qt, e->logp, e->xr, e->xd, e->cm, e->pc + L.c_fw, e->backup, e->dm, e->dcq, e->dq, e->lrow, sc, sP);
     KCHK();
-    critic_final_grads_kernel<<<1, 32, 0, st>>>(e->lrow, e->cm, e->cq.c, e->gc + L.c_fw, e->gc + L.c_fb, e->loss, B, sP);
+    critic_final_grads_kernel<<<1, 256, 0, st>>>(e->lrow, e->cm, e->cq.c, e->gc + L.c_fw, e->gc + L.c_fb, e->loss, B, sP);
     KCHK();
     // MLP backward (both critics, z = 2)
     wdot_grad_kernel<<<dim3((H2 + 127) / 128, 1, 2), 128, 0, st>>>(e->dm, 1, e->ch2, H2, e->gc + L.c_l2w, e->gc + L.c_l2b, B, H2, B, (long long)B * H2, sP, sP);
@@ -367,7 +384,7 @@ static int policy_step(sacv_engine* e, cudaStream_t st, const float* eps2, float
     if (int r = critic_mlp_forward(e, st, e->pc, e->xp, e->cs.c, e->ch1, e->ch2, e->cm, e->qpi)) return r;
     actor_loss_rows_kernel<<<(B + 127) / 128, 128, 0, st>>>(e->qpi, e->logp + B, e->cm, e->pc + L.c_fw, e->dm, e->lrow_pi, sc, sP);
     KCHK();
-    mean_kernel<<<1, 32, 0, st>>>(e->lrow_pi, e->loss + 1, B);
+    mean_kernel<<<1, 256, 0, st>>>(e->lrow_pi, e->loss + 1, B);
     KCHK();
     // back through the critics' MLPs to the action columns of their input
     outer_mask_kernel<<<dim3(nblk((long long)B * H2), 1, 2), 256, 0, st>>>(e->dm, e->pc + L.c_l2w, e->ch2, e->dh2, B, H2, B, sP, (long long)B * H2);

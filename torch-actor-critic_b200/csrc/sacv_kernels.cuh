@@ -2,8 +2,7 @@
 //
 // The visual update (BASELINE configs[4]: 3x84x84 frames, batch 256) is 61 GFLOP of convolutions per update, i.e. GEMM
 // shaped and throughput bound -- unlike the 0.6 GFLOP latency-bound MLP update that the persistent kernel of
-// sacb_device.cuh serves.  It therefore runs as a stream of ordinary launches (captured once into a CUDA graph per
-// engine): uint8 frames are gathered from the HBM ring straight into im2col form, every convolution / dense layer is one
+// sacb_device.cuh serves.  It therefore runs as a stream of ordinary launches: uint8 frames are gathered from the HBM ring straight into im2col form, every convolution / dense layer is one
 // tensor-core GEMM with a fused bias / ReLU epilogue (mma.sync m16n8k8 TF32, optionally 3xTF32 = fp32-level accuracy like the
 // MLP engine), weight gradients are split-K GEMMs with a fixed-order reduction (deterministic), col2im is a gather.
 // Activations live in [batch*pixels, channels] layout (what the GEMMs produce); the NCHW order of the reference only
@@ -231,42 +230,57 @@ __global__ void im2col_frames_kernel(const T* __restrict__ frames, const long lo
     }
 }
 
-// im2col of an activation in [B*IH*IW, C] layout (column order (c, ky, kx) = the reference's weight layout [F, C, KH, KW])
+// im2col of an activation in [B*IH*IW, C] layout.  Column order (ky, kx, c): for a fixed output pixel and ky the KW*C source
+// floats are ONE contiguous run of the activation, so the whole transform is coalesced 16-byte copies.  (The weights of
+// conv layers 1 and 2 are stored in the matching [F, KH, KW, C] order in the arena; the Python modules expose them as
+// permuted views with the reference's [F, C, KH, KW] shape.)
 __global__ void im2col_act_kernel(const float* __restrict__ act, float* __restrict__ col, int B, int C, int IH, int IW, int KH, int S,
                                   int OH, int OW) {
-    const int K = C * KH * KH;
-    const long long total = (long long)B * OH * OW * K;
+    const int seg = KH * C, K = KH * seg;
+    const int V = (C & 3) ? 1 : 4, segv = seg / V;
+    const long long total = (long long)B * OH * OW * KH * segv;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int kk = (int)(i % K); const long long pix = i / K;
-        const int kx = kk % KH, ky = (kk / KH) % KH, c = kk / (KH * KH);
-        const int ox = (int)(pix % OW); const long long r = pix / OW;
-        const int oy = (int)(r % OH); const int b = (int)(r / OH);
-        col[i] = act[((size_t)(b * IH + oy * S + ky) * IW + ox * S + kx) * C + c];
+        const int q = (int)(i % segv); long long r = i / segv;
+        const int ky = (int)(r % KH); const long long pix = r / KH;
+        const int ox = (int)(pix % OW); const long long r2 = pix / OW;
+        const int oy = (int)(r2 % OH); const int b = (int)(r2 / OH);
+        const float* src = act + ((size_t)(b * IH + oy * S + ky) * IW + ox * S) * C + (size_t)q * V;
+        float* dst = col + (size_t)pix * K + (size_t)ky * seg + (size_t)q * V;
+        if (V == 4) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+        else *dst = *src;
     }
 }
 
 // col2im as a gather + ReLU mask of the layer input: dact[b,iy,ix,c] = [act > 0] * sum over the patches that cover the pixel
+// (same (ky, kx, c) column order: consecutive channels are consecutive in dcol)
 __global__ void col2im_mask_kernel(const float* __restrict__ dcol, const float* __restrict__ act, float* __restrict__ dact, int B, int C,
                                    int IH, int IW, int KH, int S, int OH, int OW) {
     const int K = C * KH * KH;
-    const long long total = (long long)B * IH * IW * C;
+    const int V = (C & 3) ? 1 : 4, Cv = C / V;
+    const long long total = (long long)B * IH * IW * Cv;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C); long long r = i / C;
+        const int cq = (int)(i % Cv); long long r = i / Cv;
         const int ix = (int)(r % IW); r /= IW;
         const int iy = (int)(r % IH); const int b = (int)(r / IH);
-        float s = 0.f;
-        if (act[i] > 0.f) {
-            for (int ky = iy % S; ky < KH; ky += S) {
-                const int oy = (iy - ky) / S;
-                if (iy - ky < 0 || oy >= OH) continue;
-                for (int kx = ix % S; kx < KH; kx += S) {
-                    const int ox = (ix - kx) / S;
-                    if (ix - kx < 0 || ox >= OW) continue;
-                    s += dcol[((size_t)(b * OH + oy) * OW + ox) * K + (c * KH + ky) * KH + kx];
-                }
+        const size_t e = ((size_t)(b * IH + iy) * IW + ix) * C + (size_t)cq * V;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ky = iy % S; ky < KH; ky += S) {
+            const int oy = (iy - ky) / S;
+            if (iy - ky < 0 || oy >= OH) continue;
+            for (int kx = ix % S; kx < KH; kx += S) {
+                const int ox = (ix - kx) / S;
+                if (ix - kx < 0 || ox >= OW) continue;
+                const float* p = dcol + ((size_t)(b * OH + oy) * OW + ox) * K + (size_t)(ky * KH + kx) * C + (size_t)cq * V;
+                if (V == 4) { const float4 v = *reinterpret_cast<const float4*>(p); s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w; }
+                else s[0] += *p;
             }
         }
-        dact[i] = s;
+        if (V == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(act + e);
+            *reinterpret_cast<float4*>(dact + e) = make_float4(a.x > 0.f ? s[0] : 0.f, a.y > 0.f ? s[1] : 0.f, a.z > 0.f ? s[2] : 0.f, a.w > 0.f ? s[3] : 0.f);
+        } else {
+            dact[e] = act[e] > 0.f ? s[0] : 0.f;
+        }
     }
 }
 
@@ -284,15 +298,26 @@ __global__ void permute_flat_kernel(const float* __restrict__ src, const float* 
     }
 }
 
-// column sums in fixed order: out[n] = sum_m X[m*ld + n]  (bias gradients); one warp-wide strip of columns per CTA row group
-__global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int N, int ld, long long sX, long long sOut) {
+// column sums in fixed order: out[n] = sum_m X[m*ld + n]  (bias gradients); one warp-wide strip of columns per CTA row group.
+// gridDim.y > 1: row block y of `rows_per_block` rows writes its partial sums to out + y*part_stride (a second launch of the
+// same kernel over the [gridDim.y, N] partials finishes the sum) -- a conv bias gradient sums 100k rows.
+__global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int N, int ld, long long sX, long long sOut,
+                              int rows_per_block = 0, long long part_stride = 0) {
     __shared__ float red[8][33];
     const int z = blockIdx.z;
     const int n = blockIdx.x * 32 + (threadIdx.x & 31), rg = threadIdx.x >> 5;      // 8 row groups x 32 columns
     const float* x = X + (size_t)z * sX;
+    const int mb = rows_per_block ? blockIdx.y * rows_per_block : 0, me = rows_per_block ? min(M, mb + rows_per_block) : M;
+    out += (size_t)blockIdx.y * part_stride;
     float s = 0.f;
-    if (n < N)
-        for (int m = rg; m < M; m += 8) s += x[(size_t)m * ld + n];
+    if (n < N) {
+        int m = mb + rg;
+        for (; m + 24 < me; m += 32) {                  // 4 independent loads in flight
+            const float a0 = x[(size_t)m * ld + n], a1 = x[(size_t)(m + 8) * ld + n], a2 = x[(size_t)(m + 16) * ld + n], a3 = x[(size_t)(m + 24) * ld + n];
+            s += (a0 + a1) + (a2 + a3);
+        }
+        for (; m < me; m += 8) s += x[(size_t)m * ld + n];
+    }
     red[rg][threadIdx.x & 31] = s;
     __syncthreads();
     if (rg == 0 && n < N) {
@@ -424,23 +449,34 @@ __global__ void critic_loss_rows_kernel(const float* __restrict__ q, const float
     }
     lrow[(size_t)b * 4 + 0] = e[0] * e[0]; lrow[(size_t)b * 4 + 1] = e[1] * e[1];
 }
-// d loss / d final.{weight,bias} of both critics + the loss itself, fixed order, one CTA
+// d loss / d final.{weight,bias} of both critics + the loss itself: one CTA of 256 threads, 8 quantities, fixed-order tree
 __global__ void critic_final_grads_kernel(const float* __restrict__ lrow, const float* __restrict__ m, const float* __restrict__ c, float* __restrict__ gw,
                                           float* __restrict__ gb, float* __restrict__ loss_out, int B, long long sW) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float l0 = 0.f, l1 = 0.f;
-    for (int z = 0; z < 2; ++z) {
-        float g0 = 0.f, g1 = 0.f, gbz = 0.f;
-        for (int b = 0; b < B; ++b) {
+    __shared__ float red[8][256];
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // z0: g0 g1 gb | z1: g0 g1 gb | l0 l1
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
             const float dq = lrow[(size_t)b * 4 + 2 + z];
-            g0 = fmaf(dq, fmaxf(m[(size_t)z * B + b], 0.f), g0);
-            g1 = fmaf(dq, c[(size_t)z * B + b], g1);
-            gbz += dq;
+            v[3 * z + 0] = fmaf(dq, fmaxf(m[(size_t)z * B + b], 0.f), v[3 * z + 0]);
+            v[3 * z + 1] = fmaf(dq, c[(size_t)z * B + b], v[3 * z + 1]);
+            v[3 * z + 2] += dq;
         }
-        gw[(size_t)z * sW] = g0; gw[(size_t)z * sW + 1] = g1; gb[(size_t)z * sW] = gbz;
+        v[6] += lrow[(size_t)b * 4]; v[7] += lrow[(size_t)b * 4 + 1];
     }
-    for (int b = 0; b < B; ++b) { l0 += lrow[(size_t)b * 4]; l1 += lrow[(size_t)b * 4 + 1]; }
-    loss_out[0] = __fadd_rn(l0 / (float)B, l1 / (float)B);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) red[q][threadIdx.x] = v[q];
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int z = 0; z < 2; ++z) { gw[(size_t)z * sW] = red[3 * z][0]; gw[(size_t)z * sW + 1] = red[3 * z + 1][0]; gb[(size_t)z * sW] = red[3 * z + 2][0]; }
+        loss_out[0] = __fadd_rn(red[6][0] / (float)B, red[7][0] / (float)B);
+    }
 }
 
 // actor loss rows (sac/algorithm.py:40-41): loss terms, routing of d min(q1,q2) into dm_z = dq_z * wf_z[0] * [m_z > 0]
@@ -454,11 +490,17 @@ __global__ void actor_loss_rows_kernel(const float* __restrict__ q, const float*
     dm[(size_t)B + b] = m[(size_t)B + b] > 0.f ? dq2 * wf[sW] : 0.f;
     lrow[b] = __fsub_rn(__fmul_rn(sc.alpha, logp[b]), fminf(q1, q2));
 }
-__global__ void mean_kernel(const float* __restrict__ x, float* __restrict__ out, int B) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void mean_kernel(const float* __restrict__ x, float* __restrict__ out, int B) {      // one CTA of 256 threads, fixed-order tree
+    __shared__ float red[256];
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += x[b];
-    out[0] = s / (float)B;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) s += x[b];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0] / (float)B;
 }
 // gradient w.r.t. [mu | log_std_raw] (the MLP engine's row_ghead_tile, same formulas): dpi [B, ldp] (first A columns)
 __global__ void ghead_rows_kernel(const float* __restrict__ hm, int ldh, const float* __restrict__ eps, const float* __restrict__ dpi, int ldp,

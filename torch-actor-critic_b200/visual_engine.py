@@ -72,12 +72,22 @@ def vlayout_for(obs_dim, act_dim, vis_dim, hidden_sizes, **kw) -> SacvLayout:
 def _cnn_spec(lay, base, prefix, vis_c, filters, kernels, dense):
     spec, cin = {}, vis_c
     for i in range(3):
-        spec[f"{prefix}conv_{i}.weight"] = (base + lay.cnn_w[i], (filters[i], cin, kernels[i], kernels[i]))
+        # conv 0 is stored [F, C, KH, KW] like the reference; conv 1 / 2 are stored [F, KH, KW, C] (channels innermost: the
+        # im2col of a [pixels, channels] activation is then contiguous copies) and exposed as a permuted view of that shape
+        spec[f"{prefix}conv_{i}.weight"] = (base + lay.cnn_w[i], (filters[i], cin, kernels[i], kernels[i]) if i == 0 else
+                                            ("nhwc", filters[i], cin, kernels[i], kernels[i]))
         spec[f"{prefix}conv_{i}.bias"] = (base + lay.cnn_b[i], (filters[i],))
         cin = filters[i]
     spec[f"{prefix}linear.weight"] = (base + lay.cnn_lw, (dense, lay.flat)); spec[f"{prefix}linear.bias"] = (base + lay.cnn_lb, (dense,))
     spec[f"{prefix}final.weight"] = (base + lay.cnn_fw, (1, dense)); spec[f"{prefix}final.bias"] = (base + lay.cnn_fb, (1,))
     return spec
+
+
+def _view(arena, o, s):
+    if s[0] == "nhwc":
+        _, f, c, kh, kw = s
+        return arena[o:o + f * c * kh * kw].view(f, kh, kw, c).permute(0, 3, 1, 2)
+    return arena[o:o + int(np.prod(s))].view(*s)
 
 
 def vactor_views(lay, arena, obs_dim, act_dim, vis_c, hidden, filters=FILTERS, kernels=KERNELS, dense=DENSE):
@@ -88,7 +98,7 @@ def vactor_views(lay, arena, obs_dim, act_dim, vis_c, hidden, filters=FILTERS, k
     spec.update(_cnn_spec(lay, lay.a_cnn, "visual_network.", vis_c, filters, kernels, dense))
     spec.update({"mu_layer.weight": (lay.a_muw, (act_dim, h2 + 1)), "mu_layer.bias": (lay.a_mub, (act_dim,)),
                  "log_std_layer.weight": (lay.a_lsw, (act_dim, h2 + 1)), "log_std_layer.bias": (lay.a_lsb, (act_dim,))})
-    return {k: arena[o:o + int(np.prod(s))].view(*s) for k, (o, s) in spec.items()}
+    return {k: _view(arena, o, s) for k, (o, s) in spec.items()}
 
 
 def vcritic_views(lay, arena, obs_dim, act_dim, vis_c, hidden, filters=FILTERS, kernels=KERNELS, dense=DENSE):
@@ -101,7 +111,7 @@ def vcritic_views(lay, arena, obs_dim, act_dim, vis_c, hidden, filters=FILTERS, 
                 f"{q}.layers.2.weight": (b + lay.c_l2w, (1, h2)), f"{q}.layers.2.bias": (b + lay.c_l2b, (1,)),
                 f"{q}.final.weight": (b + lay.c_fw, (1, 2)), f"{q}.final.bias": (b + lay.c_fb, (1,))}
         spec.update(_cnn_spec(lay, b + lay.c_cnn, f"{q}.visual_network.", vis_c, filters, kernels, dense))
-        out.update({k: arena[o:o + int(np.prod(s))].view(*s) for k, (o, s) in spec.items()})
+        out.update({k: _view(arena, o, s) for k, (o, s) in spec.items()})
     return out
 
 
