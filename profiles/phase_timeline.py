@@ -25,6 +25,12 @@ PHASES_UNFUSED = ["gather(first only)", "A.L0+C.L0q1", "A.L1+C.L1q1+C.L0q2", "A.
                   "dpi", "row_ghead", "A.dWh+dh2", "A.dW1+dh1", "A.dW0+losspi", "adam_a+gather(k+1)"]
 
 
+# folded program (csrc/sacb_fold.cuh): 2 first-update-only phases + 8 phases per update (one GPU)
+PHASES_FOLD = ["gather(first only)", "C.L1[s,a](first only)", "F1 A.L1(+L0,heads pp)", "F2 T.L1(+heads rows,L0)", "F3 C.dh1(+backup rows)",
+               "F4 C.dW1+dW0+Adam+loss_q", "F5 Cpi.L1(+pi rows,L0)+gather(k+1)", "F6 Cpi.dh1(+minQ rows,dpi pp)", "F7 A.dh1(+ghead rows)+C.L1(k+1)",
+               "F8 A.dW+Adam+C.L1(k+1)"]
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     from torch_actor_critic_b200.engine import Engine, actor_views, critic_views
@@ -50,7 +56,8 @@ def main():
     torch.cuda.synchronize()
     st = eng.profile_phases(n).astype(np.int64)              # [n, P, ctas, 2]
     nP, nC = st.shape[1], st.shape[2]
-    names = PHASES if nP == len(PHASES) else PHASES_UNFUSED if nP == len(PHASES_UNFUSED) else [f"p{i}" for i in range(nP)]
+    names = (PHASES if nP == len(PHASES) else PHASES_UNFUSED if nP == len(PHASES_UNFUSED) else PHASES_FOLD if nP == len(PHASES_FOLD)
+             else [f"p{i}" for i in range(nP)])
     work_end = st[..., 0].max(axis=2)                        # slowest CTA done with its tiles
     bar_end = st[..., 1].max(axis=2)                         # everyone past the barrier
     first_work_end = np.where(st[..., 0] > 0, st[..., 0], np.iinfo(np.int64).max).min(axis=2)
