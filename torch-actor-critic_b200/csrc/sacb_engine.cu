@@ -116,7 +116,6 @@ struct sacb_engine {
         *dh2, *dh1, *dpi, *ghead, *hpart, *dpart, *adh2, *adh1, *lparts_q, *lparts_pi, *loss_scalar, *ga, *gc;
     // folded program only: critic activations of the actor-loss pass, its Q-dot partials, per-row-block column-sum partials
     float *cp1, *cp2, *qppart, *colp_b0, *colp_b1, *colp_w2, *colp_ab0, *colp_ab1, *colp_bh;
-    float *mb_c2, *mb_p2, *mb_a2;   // ReLU sign-bit words (uint32 stored in the float workspace)
     int row_blocks = 0;
     bool fold_ok = false;           // the folded program exists for this configuration / arithmetic path
     int last_parity = 0;            // staging parity of the last update executed (debug reads of the folded program)
@@ -355,7 +354,6 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
         f.qbuf = e->qbuf; f.lparts_q = e->lparts_q; f.lparts_pi = e->lparts_pi;
         f.dh2 = e->dh2; f.colp_b1 = e->colp_b1; f.colp_w2 = e->colp_w2;
         f.dpart = e->dpart; f.ghead = e->ghead; f.adh2 = e->adh2; f.colp_ab1 = e->colp_ab1; f.colp_bh = e->colp_bh;
-        f.mb_c2 = (const unsigned*)e->mb_c2; f.mb_p2 = (const unsigned*)e->mb_p2; f.mb_a2 = (const unsigned*)e->mb_a2; f.ch2 = e->ch2;
     }
 }
 
@@ -459,7 +457,6 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     want(e->cp1, B * 2 * H1); want(e->cp2, B * 2 * H2); want(e->qppart, 2LL * tn16_H2 * B);
     want(e->colp_b0, RB * 2 * H1); want(e->colp_b1, RB * 2 * H2); want(e->colp_w2, RB * 2 * H2);
     want(e->colp_ab0, RB * H1); want(e->colp_ab1, RB * H2); want(e->colp_bh, RB * 16);
-    want(e->mb_c2, 2 * B * tn16_H2); want(e->mb_p2, 2 * B * tn16_H2); want(e->mb_a2, B * tn16_H2);
     want(e->ah1, B * H1); want(e->ah2, B * H2); want(e->heads, B * e->ldh); want(e->logp, 2 * B);
     want(e->ch1, B * 2 * H1); want(e->ch2, B * 2 * H2); want(e->th1, B * 2 * H1); want(e->th2, B * 2 * H2);
     want(e->qpart, 2LL * tn16_H2 * B); want(e->qtpart, 2LL * tn16_H2 * B); want(e->qbuf, 9 * B); want(e->qfw, 2 * B);

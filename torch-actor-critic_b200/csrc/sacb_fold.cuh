@@ -96,16 +96,7 @@ __device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* 
         cp_async_commit();
     }
     TR(130);
-    // 2. input rows, transposed: XsT[k][m].  For the target critic / the critic of the actor loss the action columns are the
-    //    policy's own sample (networks/linear.py:37-51; pass 0 = a2 with eps1, pass 1 = pi with eps2; 8 lanes per row, lane
-    //    a < A): its head partial sums are requested together with the state rows, the state columns are multiplied while
-    //    those loads are in flight, then the sample is evaluated and its columns are added.
-    const bool heads = src == 1 || src == 2;
-    const int pass = src == 2 ? 1 : 0;
-    const float* eps = nullptr;
-    const int hm = t >> 3, ha = t & 7, hrow = row0 + hm;
-    const bool hactive = heads && t < 256 && hm < i_valid && ha < A;
-    float pm[8], pl[8], hmu = 0.f, hls = 0.f, heps = 0.f;
+    // 2. input rows, transposed: XsT[k][m] (all loads in flight before the first store)
     {
         float xv[4];
 #pragma unroll
@@ -113,20 +104,6 @@ __device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* 
             const int e = t + u * kThreads;
             const int m = e / ncopy, c = e - m * ncopy;
             xv[u] = (e < 32 * ncopy && m < i_valid) ? __ldcg(Xg + (size_t)(row0 + m) * ldX + c) : 0.f;
-        }
-        if (heads) {
-            eps = pass ? ra.eps2 : ra.eps1;
-            if (eps) eps += (size_t)kk * ra.eps_stride;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const bool ok = hactive && u < f.tnH2;
-                pm[u] = ok ? __ldcg(f.hpart + ((size_t)u * 2 * A + ha) * B + hrow) : 0.f;
-                pl[u] = ok ? __ldcg(f.hpart + ((size_t)u * 2 * A + A + ha) * B + hrow) : 0.f;
-            }
-            if (hactive) {
-                hmu = __ldcg(f.a_bh + ha); hls = __ldcg(f.a_bh + A + ha);
-                heps = eps ? __ldg(eps + (size_t)hrow * A + ha) : 0.f;
-            }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -136,12 +113,46 @@ __device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* 
         }
     }
     TR(131);
+    // 2b. action columns = the policy's own sample (networks/linear.py:37-51): pass 0 (a2, eps1) for the target critic,
+    //     pass 1 (pi, eps2) for the critic of the actor loss.  8 lanes per row, lane a < A.
+    if (src == 1 || src == 2) {
+        const int pass = src == 2 ? 1 : 0;
+        const float* eps = pass ? ra.eps2 : ra.eps1;
+        if (eps) eps += (size_t)kk * ra.eps_stride;
+        if (t < 256) {
+            const int m = t >> 3, a = t & 7, row = row0 + m;
+            const bool active = m < i_valid && a < A;
+            float sl = 0.f, sc = 0.f, act = 0.f, mu = 0.f, lsr = 0.f;
+            if (active) {
+                heads_from_partials(f, A, B, row, a, mu, lsr);
+                const float e = eps ? __ldg(eps + (size_t)row * A + a) : 0.f;
+                const HeadVals h = head_eval(mu, lsr, e, eps == nullptr, ra);
+                act = __fmul_rn(h.th, ra.act_limit);
+                sl = h.logp_term; sc = h.corr_term;
+            }
+            if (a < A) XsT[(O + a) * 32 + m] = act;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                sl += __shfl_xor_sync(0xffffffffu, sl, o);
+                sc += __shfl_xor_sync(0xffffffffu, sc, o);
+            }
+            if (col0 && z == 0 && m < i_valid) {
+                if (a == 0) f.logp[pass * B + row] = __fsub_rn(sl, sc);
+                if (a < A) {
+                    f.heads[(size_t)row * f.ldh + a] = mu;            // [mu | log_std_raw] for the head-gradient rows
+                    f.heads[(size_t)row * f.ldh + A + a] = lsr;
+                    (pass ? f.dbg_pi : f.dbg_a2)[(size_t)row * f.ldx + a] = act;
+                }
+            }
+        }
+    }
+    TR(132);
     const int cg = t & 63, rg = t >> 6;                     // this thread's column group / row group (kThreads == 256)
     float bias[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bias[j] = (cg + 64 * j < H1) ? __ldcg(b0g + cg + 64 * j) : 0.f;
     if (!bulk) cp_async_wait<0>();
-    __syncthreads();                                        // X^T state columns complete; the mbarrier's init is visible to every thread
+    __syncthreads();                                        // X^T complete; the mbarrier's init is visible to every thread
     if (bulk) mbar_wait(mbar, 0);
     TR(133);
     // 3. h1[m][n] = relu(b0[n] + x[m] . W0[n]) for the tile's 32 rows, fp32 FFMA, k ascending
@@ -150,13 +161,13 @@ __device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* 
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    // columns beyond H1 read (finite) stale shared memory and are masked below
-    const float* w0 = W0s + cg * pitchW;
-    const int cstride = 64 * pitchW;
-    const float* xr = XsT + 8 * rg;
-    auto fma_cols = [&](int kb, int ke) {
+    {
+        // columns beyond H1 read (finite) stale shared memory and are masked below
+        const float* w0 = W0s + cg * pitchW;
+        const int cstride = 64 * pitchW;
+        const float* xr = XsT + 8 * rg;
 #pragma unroll 1
-        for (int k = kb; k < ke; ++k) {
+        for (int k = 0; k < K0; ++k) {
             const float4 xa = *reinterpret_cast<const float4*>(xr + k * 32);
             const float4 xb = *reinterpret_cast<const float4*>(xr + k * 32 + 4);
             const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
@@ -168,36 +179,6 @@ __device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x[i], w[j], acc[i][j]);
         }
-    };
-    fma_cols(0, ncopy);
-    if (heads) {
-        if (t < 256) {
-            float sl = 0.f, sc = 0.f, act = 0.f;
-            if (hactive) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { hmu += pm[u]; hls += pl[u]; }         // bias first, tiles in order (as row_heads_tile)
-                const HeadVals h = head_eval(hmu, hls, heps, eps == nullptr, ra);
-                act = __fmul_rn(h.th, ra.act_limit);
-                sl = h.logp_term; sc = h.corr_term;
-            }
-            if (ha < A) XsT[(O + ha) * 32 + hm] = act;
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                sl += __shfl_xor_sync(0xffffffffu, sl, o);
-                sc += __shfl_xor_sync(0xffffffffu, sc, o);
-            }
-            if (col0 && z == 0 && hm < i_valid) {
-                if (ha == 0) f.logp[pass * B + hrow] = __fsub_rn(sl, sc);
-                if (ha < A) {
-                    f.heads[(size_t)hrow * f.ldh + ha] = hmu;            // [mu | log_std_raw] for the head-gradient rows
-                    f.heads[(size_t)hrow * f.ldh + A + ha] = hls;
-                    (pass ? f.dbg_pi : f.dbg_a2)[(size_t)hrow * f.ldx + ha] = act;
-                }
-            }
-        }
-        __syncthreads();
-        TR(132);
-        fma_cols(ncopy, K0);
     }
     TR(134);
     const bool wr_out = col0 && gwrite && Hout != nullptr;
@@ -220,7 +201,7 @@ __device__ __forceinline__ void gen_l0(const Job& jb, const RunArgs& ra, float* 
 // GEN_BACKUP / GEN_PI: the loss rows (row_loss_tile) computed per tile, dh2 generated in place over the relu-mask tile
 // ----------------------------------------------------------------------------------------------------------
 template <bool IS_PI>
-__device__ __forceinline__ void gen_loss(const Job& jb, const RunArgs& ra, float* smem, int i0, int i_valid, int z, int ti, bool col0, bool col1, int k) {
+__device__ __forceinline__ void gen_loss(const Job& jb, const RunArgs& ra, float* smem, int i0, int i_valid, int z, int ti, bool col0, int k) {
     const FoldPtrs& f = ra.f;
     float* misc = smem + kPipeFloats + kGenMisc;
     float* dqs = misc;                                      // [2][32]
@@ -228,11 +209,13 @@ __device__ __forceinline__ void gen_loss(const Job& jb, const RunArgs& ra, float
     const int H2 = jb.K, B = ra.B, nt = f.tnH2;
     float* const dh2g = f.dh2; float* const colp_b1 = f.colp_b1; float* const colp_w2 = f.colp_w2;
     const size_t par = (size_t)(k & 1);
-    // ReLU mask of layer 1 (this z): the sign bits its producer tiles published, 1 KB instead of the 32 KB activation tile
-    unsigned* mks = reinterpret_cast<unsigned*>(misc + 256);   // [32 rows][nt words]
+    // relu-mask tile (forward activations of layer 1, this z) -> the A stage buffers
     {
-        const unsigned* mb = (IS_PI ? f.mb_p2 : f.mb_c2) + ((size_t)z * B + i0) * nt;
-        if (t < 32 * nt) mks[t] = (t / nt) < i_valid ? __ldcg(mb + t) : 0u;
+        const float* Ag = jb.A + (size_t)z * jb.sA;
+        const int lda = jb.lda, a_vec = jb.a_vec;
+        const int nst = (H2 + kBK - 1) / kBK;
+        for (int s = 0; s < nst; ++s) load_operand<true>(stage_a(smem, s), Ag, lda, i0, i_valid, s * kBK, min(kBK, H2 - s * kBK), a_vec);
+        cp_async_commit();
     }
     TR(120);
     // per-row scalars: 8 lanes per row (lane tt sums partial tile tt of every net), all loads of the tile in flight at once
@@ -303,6 +286,7 @@ __device__ __forceinline__ void gen_loss(const Job& jb, const RunArgs& ra, float
     TR(121);
     const int n = t;
     const float w2 = n < H2 ? __ldcg(f.c_w2 + (size_t)z * H2 + n) : 0.f;
+    cp_async_wait<0>();
     __syncthreads();
     TR(122);
     if (col0 && z == 0 && t < 4) {                          // fixed summation order over the tile's rows (deterministic losses)
@@ -315,36 +299,34 @@ __device__ __forceinline__ void gen_loss(const Job& jb, const RunArgs& ra, float
     if (n < H2r) {
         float* col = stage_a(smem, n >> 6) + (n & 63);
         const bool wr = !IS_PI && col0 && n < H2;
-        // 4 rows per iteration, rolled (a fully unrolled version measured slower).  The column sums that become db1 (tiles of
-        // column 0) and dW2 (tiles of column 1, which read the activation values for it) are spread over two tile columns.
+        // Rolled on purpose: a fully unrolled version of this loop (650 instructions) measured 6.3k cycles against 3.4k.
+        // 4 rows per iteration, every shared-memory load before the first store (col[] and dq[] may alias for the compiler).
         float cs_b1 = 0.f, cs_w2 = 0.f;
         const float* dqz = dqs + z * 32;
-        const int wsel = n >> 5, bsel = n & 31;
-        const bool w2t = !IS_PI && col1 && n < H2;
-        const float* hg = f.ch2 + (size_t)i0 * 2 * H2 + (size_t)z * H2 + n;
 #pragma unroll 1
         for (int m0 = 0; m0 < 32; m0 += 4) {
             const float4 d4 = *reinterpret_cast<const float4*>(dqz + m0);
             const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-            unsigned wv[4];
-            float hv[4] = {0.f, 0.f, 0.f, 0.f};
+            float h[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) wv[u] = mks[(m0 + u) * nt + wsel];
-            if (w2t) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) if (m0 + u < i_valid) hv[u] = __ldcg(hg + (size_t)(m0 + u) * 2 * H2);
-            }
+            for (int u = 0; u < 4; ++u) h[u] = col[(m0 + u) * kPitchRC];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int m = m0 + u;
-                const float v = (n < H2 && ((wv[u] >> bsel) & 1u)) ? d[u] * w2 : 0.f;
+                const bool ok = n < H2 && m < i_valid;
+                const float v = (ok && h[u] > 0.f) ? d[u] * w2 : 0.f;
                 col[m * kPitchRC] = v;
-                if (wr && m < i_valid) { dh2g[(size_t)(i0 + m) * 2 * H2 + (size_t)z * H2 + n] = v; cs_b1 += v; }
-                cs_w2 = fmaf(d[u], hv[u], cs_w2);
+                if (wr && m < i_valid) {
+                    dh2g[(size_t)(i0 + m) * 2 * H2 + (size_t)z * H2 + n] = v;
+                    cs_b1 += v;
+                    cs_w2 = fmaf(d[u], h[u], cs_w2);
+                }
             }
         }
-        if (w2t) colp_w2[(size_t)ti * 2 * H2 + (size_t)z * H2 + n] = cs_w2;            // partial of d loss / d W2[z][n]
-        if (wr) colp_b1[(size_t)ti * 2 * H2 + (size_t)z * H2 + n] = cs_b1;            // partial of d loss / d b1[z][n]
+        if (wr) {
+            colp_b1[(size_t)ti * 2 * H2 + (size_t)z * H2 + n] = cs_b1;        // partial of d loss / d b1[z][n]
+            colp_w2[(size_t)ti * 2 * H2 + (size_t)z * H2 + n] = cs_w2;        // partial of d loss / d W2[z][n]
+        }
     }
     __syncthreads();
 }
@@ -358,9 +340,13 @@ __device__ __forceinline__ void gen_ghead(const Job& jb, const RunArgs& ra, floa
     const int t = threadIdx.x;
     const int H2 = jb.K, A = ra.A, B = ra.B, twoA = 2 * A;
     float* const adh2g = f.adh2;
-    const int nt = f.tnH2;
-    unsigned* mks = reinterpret_cast<unsigned*>(ghs + 512);   // [32 rows][nt words]: ReLU sign bits of ah2 (published by the A.L1 tiles)
-    if (t < 32 * nt) mks[t] = (t / nt) < i_valid ? __ldcg(f.mb_a2 + (size_t)i0 * nt + t) : 0u;
+    {
+        const float* Ag = jb.A;
+        const int lda = jb.lda, a_vec = jb.a_vec;
+        const int nst = (H2 + kBK - 1) / kBK;
+        for (int s = 0; s < nst; ++s) load_operand<true>(stage_a(smem, s), Ag, lda, i0, i_valid, s * kBK, min(kBK, H2 - s * kBK), a_vec);
+        cp_async_commit();
+    }
     const int cg = t & 63, rg = t >> 6;
     // head weights of this thread's 4 columns: wh[j][c] = Wh[j][cg + 64 c]
     float wh[16][4];
@@ -396,6 +382,7 @@ __device__ __forceinline__ void gen_ghead(const Job& jb, const RunArgs& ra, floa
             for (int j = twoA; j < 16; ++j) ghs[m * 16 + j] = 0.f;    // unused tail of the row: finite (it meets zero weights)
     }
     TR(141);
+    cp_async_wait<0>();
     __syncthreads();
     TR(142);
     if (col0 && t < twoA) {                                 // partial of d loss / d b_heads[t]
@@ -413,16 +400,16 @@ __device__ __forceinline__ void gen_ghead(const Job& jb, const RunArgs& ra, floa
         const float4 g0 = *reinterpret_cast<const float4*>(gr), g1 = *reinterpret_cast<const float4*>(gr + 4),
                      g2 = *reinterpret_cast<const float4*>(gr + 8), g3 = *reinterpret_cast<const float4*>(gr + 12);
         const float g[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
-        unsigned wv[4];
+        float hv[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wv[c] = (cg + 64 * c < H2) ? mks[m * nt + ((cg + 64 * c) >> 5)] : 0u;
+        for (int c = 0; c < 4; ++c) hv[c] = (stage_a(smem, c) + cg)[m * kPitchRC];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             float a = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) a = fmaf(g[j], wh[j][c], a);   // j ascending; entries beyond 2A are zero
             const int n = cg + 64 * c;
-            const float o = (n < H2 && m < i_valid && ((wv[c] >> (cg & 31)) & 1u)) ? a : 0.f;
+            const float o = (n < H2 && m < i_valid && hv[c] > 0.f) ? a : 0.f;
             (stage_a(smem, c) + cg)[m * kPitchRC] = o;
             if (col0 && n < H2 && m < i_valid) { adh2g[(size_t)(i0 + m) * H2 + n] = o; cs[c] += o; }
         }

@@ -369,7 +369,6 @@ static void build_programs(sacb_engine* e) {
                                e->ch2 + (size_t)row0 * 2 * H2, 2 * H2, H2, nrows, H2, H1, 2);
                 j.bias = PC + L.critic_b1[0]; j.sBias = H2; j.aux0 = PC + L.critic_w2[0]; j.sAux = H2;
                 j.out0 = e->qpart + row0; j.i0 = B; j.b_static = 1; j.k_offset = k_offset;
-                j.mbits = (unsigned*)e->mb_c2;
                 return gen_job(j, GEN_L0, 3, 1, row0); };
             auto reduce_q = [&]() {
                 Job j = Builder::zero();
@@ -391,7 +390,6 @@ static void build_programs(sacb_engine* e) {
                 Job j = b.gemm(G_FWD, E_BIAS_RELU, nullptr, H1, 0, PA + L.actor_w1, H1, 0, e->ah2, H2, 0, B, H2, H1, 1);
                 j.bias = PA + L.actor_b1; j.b_static = 0;              // W1 was stepped by the previous phase (F8 of update k-1)
                 j.i1 = 2 * A; j.aux1 = PA + L.actor_w_mu; j.i2 = H2; j.i3 = 0; j.out1 = e->hpart; j.i0 = B;
-                j.mbits = (unsigned*)e->mb_a2;
                 b.add(gen_job(j, GEN_L0, 0, 1));
             }
             {   // F2
@@ -425,7 +423,6 @@ static void build_programs(sacb_engine* e) {
                 Job j = b.gemm(G_FWD, E_BIAS_RELU_DOT, nullptr, 2 * H1, H1, PC + L.critic_w1[0], H1, sW1, e->cp2, 2 * H2, H2, B, H2, H1, 2);
                 j.bias = PC + L.critic_b1[0]; j.sBias = H2; j.aux0 = PC + L.critic_w2[0]; j.sAux = H2;
                 j.out0 = e->qppart; j.i0 = B; j.b_static = 0;          // critic weights were just stepped
-                j.mbits = (unsigned*)e->mb_p2;
                 b.add(gen_job(j, GEN_L0, 2, 1));
                 b.add(gather_f(1, 2));
             }
