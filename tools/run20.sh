@@ -9,3 +9,5 @@ for cta in (3,16,140):
     s=idx[1] if len(idx)>1 else 0
     print("CTA",cta, ";".join(f"{a} {b}" for a,b in ev[s:s+135]))
 PY
+SACB_WORKLOAD=c2 SACB_PRECISION=3 python profiles/phase_timeline.py 6 > gpurun_out/r2_tl_c2_bf16.txt 2>&1
+cat gpurun_out/r2_tl_c2_bf16.txt

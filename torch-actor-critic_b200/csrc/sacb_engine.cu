@@ -2,6 +2,7 @@
 // declared in include/sacb200.h.  Compile: nvcc -gencode arch=compute_100a,code=sm_100a (see __graft_entry__.build).
 #include "sacb_device.cuh"
 
+#include <cuda.h>                  // CUtensorMap types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -133,6 +134,16 @@ struct sacb_engine {
     Phase* d_phases = nullptr;
     size_t d_jobs_cap = 0, d_phases_cap = 0;
     ProgRange p_update, p_policy, p_targets, p_actor_fwd, p_critic_fwd[2], p_fold;
+    // bf16 shadows of the GEMM operands + their tensor maps (precision 3, csrc/sacb_tma.cuh)
+    struct ShReg { const float* base; long long rows; int ld, cols; long long off16; int ld16; };
+    std::vector<ShReg> shreg;                   // fp32 region -> shadow
+    std::vector<CUtensorMap> tmaps;
+    unsigned short* sh16 = nullptr; size_t sh16_elems = 0;
+    void* d_tmaps = nullptr; size_t d_tmaps_cap = 0;
+    Sh16 sh{};
+    bool bf_tma = false;                        // precision 3 and every GEMM operand of every program is shadowed
+    int n_refresh = 0;                          // regions the pre-launch refresh kernel converts (weights + staging tiles)
+    void* d_refresh = nullptr;
     int ph_crit_begin = 0, ph_crit_adam = 0, ph_pi_begin = 0, ph_pi_adam = 0;   // split points inside p_update
     // store staging
     uint8_t* stage = nullptr;
@@ -229,10 +240,12 @@ struct Builder {
 };
 
 #include "sacb_program.inl"
+#include "sacb_tma_host.inl"
 
 static int upload_programs(sacb_engine* e, cudaStream_t st) {
     if (!e->dirty) return 0;
     build_programs(e);
+    if (int r = build_tma(e, st)) return r;
     if (e->jobs.size() > e->d_jobs_cap) {
         if (e->d_jobs) CU(cudaFree(e->d_jobs));
         e->d_jobs_cap = e->jobs.size() + 16;
@@ -337,6 +350,7 @@ static void fill_args(sacb_engine* e, RunArgs& ra) {
     ra.O = c.obs_dim; ra.A = c.act_dim; ra.H1 = c.hidden1; ra.H2 = c.hidden2; ra.B = c.batch_size;
     ra.s2_stride = (long long)c.batch_size * e->lds;
     ra.pass_mask = 3;
+    if (e->bf_tma && e->tf32x3 == 3) ra.sh = e->sh;
     {   // the folded program's generators (sacb_fold.cuh)
         const sacb_layout_info& L = e->lay;
         FoldPtrs& f = ra.f;
@@ -364,6 +378,7 @@ static int run_phases(sacb_engine* e, RunArgs ra, int pb, int pe, int kb, int ke
         const int nj = e->phases[pe - 1].job_begin + e->phases[pe - 1].job_count - e->phases[pb].job_begin;
         if (nj > kMaxJobs || pe - pb > kMaxPhases) return fail(SACB_ERR_INVALID, "program slice too large (%d jobs, %d phases)", nj, pe - pb);
     }
+    if (ra.sh.base) refresh_shadows(e, st);          // weights / staging tiles may have been written by the host side since
     const bool single = (pe - pb == 1) && (ke - kb == 1);
     if (e->mode == 1 || single) {
         for (int k = kb; k < ke; ++k)
@@ -489,7 +504,7 @@ int sacb_destroy(sacb_handle e) {
     for (int r = 0; r < kMaxPeers; ++r)
         if (e->peer_mode && e->peer_ws[r] && r != e->rank) cudaIpcCloseMemHandle(e->peer_ws[r]);
     cudaFree(e->ws); cudaFree(e->idx_buf); cudaFree(e->perm_buf); cudaFree(e->eps_buf); cudaFree(e->barrier);
-    cudaFree(e->d_jobs); cudaFree(e->d_phases);
+    cudaFree(e->d_jobs); cudaFree(e->d_phases); cudaFree(e->sh16); cudaFree(e->d_tmaps); cudaFree(e->d_refresh);
     if (e->stage) cudaFreeHost(e->stage);
     if (e->abort_host) cudaFreeHost(e->abort_host);
     if (e->stage_ev) cudaEventDestroy(e->stage_ev);
