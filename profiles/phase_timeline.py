@@ -37,6 +37,7 @@ def main():
     O, A, H, B, N = 17, 6, [256, 256], 256, 1_000_000
     if os.environ.get("SACB_WORKLOAD", "c1") == "c2":           # Humanoid shapes (BASELINE configs[2])
         O, A, H, B, N = 376, 17, [512, 512], 1024, 200_000
+    B = int(os.environ.get("SACB_BATCH", B))                    # experiment knob (working-set studies)
     eng = Engine(O, A, H, batch_size=B, max_burst=50, device=0, act_limit=1.0)
     dev = eng.tdev()
     pa, pc = eng.new_actor_arena(), eng.new_critic_arena()

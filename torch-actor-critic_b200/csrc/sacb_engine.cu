@@ -475,7 +475,7 @@ int sacb_create(const sacb_config* cfg, sacb_handle* out) {
     want(e->ah1, B * H1); want(e->ah2, B * H2); want(e->heads, B * e->ldh); want(e->logp, 2 * B);
     want(e->ch1, B * 2 * H1); want(e->ch2, B * 2 * H2); want(e->th1, B * 2 * H1); want(e->th2, B * 2 * H2);
     want(e->qpart, 2LL * tn16_H2 * B); want(e->qtpart, 2LL * tn16_H2 * B); want(e->qbuf, 9 * B); want(e->qfw, 2 * B);
-    want(e->dh2, B * 2 * H2); want(e->dh1, B * 2 * H1); want(e->dpi, B * e->lddpi); want(e->ghead, B * e->ldh);
+    want(e->dh2, B * 2 * H2); want(e->dh1, B * 2 * H1); want(e->dpi, 2 * B * e->lddpi); want(e->ghead, B * e->ldh);
     want(e->adh2, B * H2); want(e->adh1, B * H1);
     want(e->hpart, tn16_H2 * 2 * A * B); want(e->dpart, 2LL * tn16_H1 * A * B);
     want(e->lparts_q, 4LL * e->row_tiles); want(e->lparts_pi, 4LL * e->row_tiles); want(e->loss_scalar, 4);

@@ -121,7 +121,7 @@ static void build_programs(sacb_engine* e) {
         j.type = J_ADAM;
         if (critic) { j.C = PC; j.A = GC; j.out0 = e->mc; j.out1 = e->vc; j.out2 = PT; j.K = (int)L.critic_floats; j.i0 = 1; }
         else { j.C = PA; j.A = GA; j.out0 = e->ma; j.out1 = e->va; j.out2 = nullptr; j.K = (int)L.actor_floats; j.i0 = 0; }
-        j.ntiles = (j.K + kThreads * 4 - 1) / (kThreads * 4);
+        j.ntiles = (j.K + kAdamTile - 1) / kAdamTile;
         j.i2 = 1;                                  // gradient comes from the data-parallel exchange when one is active
         return j; };
     auto peer_signal = [&](bool critic) {
@@ -159,9 +159,16 @@ static void build_programs(sacb_engine* e) {
         // tile budget: one round = one tile per SM.  A.L0 + C.L0[q1] (e.g. 64 + 64 tiles) now, C.L0[q2] rides as the
         // cheap second tile of the next phase (its consumer C.L1[q2] runs one phase later anyway)
         b.phase(); b.add(actor_l0(dyn, l0_static, from_states)); if (with_critic) b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 0));
+        // large tiles (bf16: 128x64): A.L1 + C.L1[q1] + C.L0[q2] would need a second round (3 x 64 tiles at C2), so both
+        // halves of C.L1 ride with the (8-tile) heads GEMM one phase later instead
+        const int t_heads = ((B + e->tile_m - 1) / e->tile_m) * ((2 * A + e->tile_n - 1) / e->tile_n);
+        const bool l1_late = with_critic && !fuse_heads && 2 * t_l1 + t_l0 > cap && t_l1 + t_l0 <= cap && t_heads + 2 * t_l1 <= cap;
         b.phase(); b.add(actor_l1(dyn));
-        if (with_critic) { b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 1)); b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 1)); }
-        if (!fuse_heads) { b.phase(); b.add(actor_heads(dyn)); if (with_critic) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1)); }
+        if (with_critic) { if (!l1_late) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 1)); b.add(critic_l0(PC, e->xs, e->ch1, 0, 1, 1)); }
+        if (!fuse_heads) {
+            b.phase(); b.add(actor_heads(dyn));
+            if (with_critic) b.add(l1_late ? critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 0, 2) : critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1));
+        }
         b.phase(); b.add(row_heads(dyn, passes));
         if (with_critic && fuse_heads) b.add(critic_l1(PC, e->ch1, e->ch2, e->qpart, 0, 1, 1));
     };
@@ -181,7 +188,9 @@ static void build_programs(sacb_engine* e) {
         b.phase(); b.add(critic_dx1(true));
         if (!fuse_dpi) {   // d pi = dh1 . W0[:, O:O+A]   (both critics at once: reduction over 2*H1)
             b.phase();
-            Job j = b.gemm(G_DX, E_STORE, e->dh1, 2 * H1, 0, PC + L.critic_w0[0] + O, OA, 0, e->dpi, lddpi, 0, B, A, 2 * H1, 1);
+            // one z per critic (K = H1 each, summed by the head-gradient rows): twice the tiles of a single K = 2*H1 product
+            Job j = b.gemm(G_DX, E_STORE, e->dh1, 2 * H1, H1, PC + L.critic_w0[0] + O, OA, (long long)H1 * OA, e->dpi, lddpi,
+                           (long long)B * lddpi, B, A, H1, 2);
             j.b_static = 1;
             b.add(j);
         }
@@ -190,6 +199,7 @@ static void build_programs(sacb_engine* e) {
             Job j = Builder::zero();
             j.type = J_ROW_GHEAD; j.M = B; j.A = e->heads; j.lda = ldh; j.B = e->dpi; j.ldb = lddpi; j.C = e->ghead; j.ldc = ldh;
             if (fuse_dpi) { j.i1 = 2 * tnH1; j.B = e->dpart; j.i2 = B; }
+            else j.sB = (long long)B * lddpi;                 // d pi = the two critics' products
             j.ntiles = (B + kRowsGhead - 1) / kRowsGhead;
             b.add(j);
         }
@@ -263,8 +273,9 @@ static void build_programs(sacb_engine* e) {
         // loss reduction) fit on the SMs the GEMM tiles leave idle: 128 + 8 + 8 + 1 = 145 tiles at C1
         b.phase();
         b.add(critic_dx1(false));
-        b.add(with_adam(b.colsum(e->dh2, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, B, 2 * H2, 1, 64), true));
-        b.add(with_adam(b.colsum(e->ch2, 2 * H2, H2, e->qbuf + 5 * (size_t)B, B, GC + L.critic_w2[0], H2, B, H2, 2, 64), true));
+        const int cw_light = e->tf32x3 == 3 ? 128 : 64;       // bf16: 128 GEMM tiles of 128x64 already; 8 + 8 + 1 more still fit one round
+        b.add(with_adam(b.colsum(e->dh2, 2 * H2, 0, nullptr, 0, GC + L.critic_b1[0], 0, B, 2 * H2, 1, cw_light), true));
+        b.add(with_adam(b.colsum(e->ch2, 2 * H2, H2, e->qbuf + 5 * (size_t)B, B, GC + L.critic_w2[0], H2, B, H2, 2, cw_light), true));
         Job j = Builder::zero();
         j.type = J_REDUCE_Q; j.A = e->lparts_q; j.i0 = row_tiles; j.out0 = e->loss_scalar; j.out1 = GC + L.critic_b2[0];
         j.out2 = GC + L.critic_b2[1]; j.ntiles = 1;

@@ -154,7 +154,7 @@ __device__ __forceinline__ void t5_split(char* hi, char* lo, int k_valid) {
 struct T5Ctx {
     unsigned tmem; unsigned mbar; unsigned phase;     // TMEM base address, mbarrier smem address, its parity
     unsigned mbar_op0, mbar_op1, phase_op;            // bf16 path: one mbarrier per operand buffer; parity bit b of phase_op
-    unsigned tm_it, tm_done;                          // TMA path (sacb_tma.cuh): K chunks issued so far (stage ring position), parity of `done`
+    unsigned tm_it, tm_done;                               // TMA path (sacb_tma.cuh): K chunks issued so far (stage ring position), parity of `done`
 };
 
 template <bool A_RC, bool B_RC>
