@@ -51,7 +51,13 @@ def main():
     s = torch.randn(N, O, device=dev); s2 = torch.randn(N, O, device=dev)
     a = torch.rand(N, A, device=dev) * 2 - 1; r = torch.randn(N, device=dev); d = torch.rand(N, device=dev) < 1e-3
     eng.set_precision(int(os.environ.get('SACB_PRECISION', '1')))
-    eng.bind_buffer(s, a, r, s2, d)
+    if os.environ.get("SACB_RING", "packed") == "packed":       # the product's ring layout (ReplayBuffer): one aligned record per row
+        pitch = (2 * O + A + 2 + 15) // 16 * 16
+        rec = torch.zeros(N, pitch, device=dev)
+        rec[:, :O] = s; rec[:, O:O + A] = a; rec[:, O + A] = r; rec[:, O + A + 1:2 * O + A + 1] = s2; rec[:, 2 * O + A + 1] = d.float()
+        eng.bind_buffer_packed(rec)
+    else:
+        eng.bind_buffer(s, a, r, s2, d)
     eng.set_buffer_state(0, N)
     eng.update(50)
     torch.cuda.synchronize()

@@ -121,9 +121,19 @@ static void build_programs(sacb_engine* e) {
         j.type = J_ADAM;
         if (critic) { j.C = PC; j.A = GC; j.out0 = e->mc; j.out1 = e->vc; j.out2 = PT; j.K = (int)L.critic_floats; j.i0 = 1; }
         else { j.C = PA; j.A = GA; j.out0 = e->ma; j.out1 = e->va; j.out2 = nullptr; j.K = (int)L.actor_floats; j.i0 = 0; }
-        j.ntiles = (j.K + kAdamTile - 1) / kAdamTile;
+        {   // one tile per CTA, each walking its share of the 1024-float groups with the next group's loads in flight
+            const int ng = (j.K + kThreads * 4 - 1) / (kThreads * 4), cap_t = e->grid_coop > 0 ? e->grid_coop : 148;
+            j.ntiles = ng < cap_t ? ng : cap_t;
+        }
         j.i2 = 1;                                  // gradient comes from the data-parallel exchange when one is active
         return j; };
+    auto l2_prefetch = [&](const float* base, long long floats, int tiles) {
+        Job j = Builder::zero();
+        j.type = J_PREFETCH; j.A = base; j.K = (int)floats; j.ntiles = tiles;
+        return j; };
+    // bf16/TMA path (separate Adam phases, large nets): the CTAs idle in the last weight-gradient phase pull the optimizer
+    // state the Adam phase is about to stream (one arena each: params, exp_avg, exp_avg_sq [, target]) into L2
+    const bool pf_adam = e->tf32x3 == 3 && !fuse_adam && e->world <= 1;
     auto peer_signal = [&](bool critic) {
         Job j = Builder::zero();
         j.type = J_PEER_SIGNAL; j.i0 = critic ? 1 : 0; j.ntiles = 1;
@@ -240,6 +250,9 @@ static void build_programs(sacb_engine* e) {
         b.phase(); dWh(); dh2();
         b.phase(); dW1(); dh1();
         b.phase(); dW0(); loss_pi();
+        if (pf_adam && e->ma && e->va) {
+            b.add(l2_prefetch(PA, L.actor_floats, 8)); b.add(l2_prefetch(e->ma, L.actor_floats, 8)); b.add(l2_prefetch(e->va, L.actor_floats, 8));
+        }
         int adam_phase = b.phase();
         if (e->peer_mode && actor_sync) b.add(peer_signal(false));
         { Job j = adam(false); if (!actor_sync) j.i2 = 0; b.add(j); }
@@ -292,6 +305,10 @@ static void build_programs(sacb_engine* e) {
         b.add(st(with_adam(b.gemm(G_DW, E_STORE, e->dh2, 2 * H2, H2, e->ch1, 2 * H1, H1, GC + L.critic_w1[0], H1, sW1, H2, H1, B, 2), true)));
         b.add(st(with_adam(b.gemm(G_DW, E_STORE, e->dh1, 2 * H1, 0, e->xs, ldx, 0, GC + L.critic_w0[0], OA, 0, 2 * H1, OA, B, 1), true)));
         b.add(with_adam(b.colsum(e->dh1, 2 * H1, 0, nullptr, 0, GC + L.critic_b0[0], 0, B, 2 * H1, 1, 128), true));
+        if (pf_adam && e->mc && e->vc) {
+            b.add(l2_prefetch(PC, L.critic_floats, 4)); b.add(l2_prefetch(e->mc, L.critic_floats, 4));
+            b.add(l2_prefetch(e->vc, L.critic_floats, 4)); b.add(l2_prefetch(PT, L.critic_floats, 4));
+        }
     }
     if (fuse_adam) {
         e->ph_crit_adam = (int)e->phases.size() - 1;        // "the phase that ends update_critic": the fused dW + Adam phase
