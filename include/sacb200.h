@@ -181,7 +181,8 @@ int sacb_peer_bind(sacb_handle h, const uint8_t* handles, int32_t rank, int32_t 
 int sacb_peer_status(sacb_handle h, uintptr_t stream);
 
 /* Test / debug: copy an internal f32 array to HOST memory (synchronous).  Names: "backup","q1","q2","q1_target",
- * "q2_target","a2","logp_next","pi","logp_pi","q1_pi","q2_pi","grad_actor","grad_critic","loss_q_parts", ...
+ * "q2_target","a2","logp_next","pi","logp_pi","q1_pi","q2_pi","grad_actor","grad_critic","loss_q_parts", ...;
+ * "operand_path" -> [1 if precision 3 feeds its GEMM tiles from bf16 shadow operands through the TMA, number of tensor maps].
  * Returns the number of floats written via *n_out. */
 int sacb_debug_read(sacb_handle h, const char* name, float* dst_host, int64_t max_floats, int64_t* n_out);
 /* Test / debug: run n_updates like sacb_update with device-drawn inputs while every CTA stamps %globaltimer after the

@@ -476,7 +476,7 @@ def test_humanoid_shaped_update_matches_oracle(tf32x3):
         grads_close(ga[k].numpy(), o["actor_grads"][k], k)
 
 
-@pytest.mark.parametrize("shape", ["humanoid", "ragged"])
+@pytest.mark.parametrize("shape", ["humanoid", "ragged", "ragged8"])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_bf16_tensor_core_path_matches_bf16_oracle(shape, mode):
     """BASELINE config 3 ("Humanoid-shaped ..., bf16 tensor-core MLP path"): precision 3 = tcgen05 GEMMs with bf16
@@ -490,8 +490,13 @@ def test_bf16_tensor_core_path_matches_bf16_oracle(shape, mode):
     entries and max |err| <= 0.1 max |g|.  "ragged": tile tails in every dimension (M < 128, N < 64, K not a multiple of 16, unaligned
     rows -> element-wise staging)."""
     from torch_actor_critic_b200.engine import Engine, actor_views, critic_views
+    # "humanoid" and "ragged8" (obs_dim a multiple of 8: every operand has a 16-byte-aligned bf16 shadow) run on the TMA-fed
+    # tiles (csrc/sacb_tma.cuh), "ragged8" with tile tails in every dimension; "ragged" (obs_dim 11) cannot be mapped and
+    # takes the staged cp.async tiles
     if shape == "humanoid":
         O, A, H, B, N, lim = 376, 17, [512, 512], 1024, 4096, 0.4
+    elif shape == "ragged8":
+        O, A, H, B, N, lim = 24, 5, [72, 40], 96, 700, 1.0
     else:
         O, A, H, B, N, lim = 11, 3, [72, 40], 96, 700, 1.0
     rng = np.random.default_rng(5)
@@ -515,6 +520,7 @@ def test_bf16_tensor_core_path_matches_bf16_oracle(shape, mode):
     t = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in arrays.items()}
     eng.bind_buffer(t["state"], t["actions"], t["rewards"], t["next_state"], t["done"])
     eng.set_buffer_state(0, N)
+    assert bool(eng.debug_read("operand_path")[0]) == (shape != "ragged")
     lq, lp = eng.update(1, idx=idx, eps=eps)
     hp = onp.HyperParams(act_limit=lim)
     a64, c64, t64 = (onp.cast_params(p, np.float64) for p in (actor, critic, critic))
@@ -545,6 +551,55 @@ def test_bf16_tensor_core_path_matches_bf16_oracle(shape, mode):
     ga = actor_views(eng.layout, torch.from_numpy(eng.debug_read("grad_actor")), O, A, H)
     for k in ACTOR_KEYS:
         grads_close(ga[k].numpy(), o["actor_grads"][k], k)
+
+
+@pytest.mark.parametrize("shape", ["humanoid", "ragged8"])
+def test_bf16_tma_operands_match_staged_operands(shape, monkeypatch):
+    """Precision 3 twice on the same seeds: GEMM operands fetched by the TMA from the bf16 shadows (csrc/sacb_tma.cuh, the
+    default) and staged through cp.async + conversion (SACB_TMA=0).  Both round the same fp32 values to bf16 and accumulate
+    in fp32; they differ in the order of the K sum (the TMA tiles keep four accumulators), i.e. by fp32 rounding, which
+    the next layer's bf16 rounding can amplify to one bf16 ulp (2^-8 relative) on isolated activations.  Stated tolerance
+    over a 3-update burst: losses rtol 1e-3, per-sample quantities 5e-3; updated parameters within 2e-5 for >= 97% of the
+    entries and within 6 lr for all (see below)."""
+    from torch_actor_critic_b200.engine import Engine, actor_views, critic_views
+    O, A, H, B, N = (376, 17, [512, 512], 1024, 4096) if shape == "humanoid" else (24, 5, [72, 40], 96, 700)
+    rng = np.random.default_rng(11)
+    actor, critic = onp.init_params(O, A, H, rng)
+    arrays = dict(state=rng.standard_normal((N, O)).astype(np.float32), actions=rng.uniform(-1, 1, (N, A)).astype(np.float32),
+                  rewards=rng.standard_normal(N).astype(np.float32), next_state=rng.standard_normal((N, O)).astype(np.float32),
+                  done=rng.random(N) < 0.05)
+    idx = np.stack([rng.choice(N, B, replace=False) for _ in range(3)])
+    eps = rng.standard_normal((3, 2, B, A)).astype(np.float32)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in arrays.items()}
+    out = {}
+    for tma in (1, 0):
+        monkeypatch.setenv("SACB_TMA", str(tma))
+        eng = Engine(O, A, H, batch_size=B, max_burst=4, device=0, act_limit=1.0)
+        eng.set_precision(3)
+        pa, pc = eng.new_actor_arena(), eng.new_critic_arena()
+        for k, v in actor_views(eng.layout, pa, O, A, H).items():
+            v.copy_(torch.from_numpy(actor[k]))
+        for k, v in critic_views(eng.layout, pc, O, A, H).items():
+            v.copy_(torch.from_numpy(critic[k]))
+        pt = pc.clone()
+        eng.bind_params(pa, pc, pt)
+        eng.bind_adam(eng.new_actor_arena(), eng.new_actor_arena(), 0, eng.new_critic_arena(), eng.new_critic_arena(), 0)
+        eng.bind_buffer(t["state"], t["actions"], t["rewards"], t["next_state"], t["done"])
+        eng.set_buffer_state(0, N)
+        assert bool(eng.debug_read("operand_path")[0]) == bool(tma)
+        lq, lp = eng.update(3, idx=idx, eps=eps)
+        out[tma] = dict(lq=lq.cpu().numpy(), lp=lp.cpu().numpy(), pa=pa.cpu().numpy(), pc=pc.cpu().numpy(), pt=pt.cpu().numpy(),
+                        q1=eng.debug_read("q1"), backup=eng.debug_read("backup"), pi=eng.debug_read("pi"))
+    a, b = out[1], out[0]
+    assert_close(a["lq"], b["lq"], 1e-3, 1e-5, "loss_q")
+    assert_close(a["lp"], b["lp"], 1e-3, 1e-5, "loss_pi")
+    for key in ("q1", "backup", "pi"):
+        assert_close(a[key], b[key], 5e-3, 5e-3, key)
+    # parameters: Adam's first steps are +-lr whatever the gradient's size, so an entry whose (tiny) gradient changes sign
+    # between the two summation orders moves by up to 2 lr per step; everything else agrees to fp32 rounding
+    for key in ("pa", "pc", "pt"):
+        d = np.abs(a[key] - b[key])
+        assert (d > 2e-5).mean() <= 3e-2 and d.max() <= 3 * 2 * 3e-4 * 1.001, f"{key}: {(d > 2e-5).mean():.3%} off, max {d.max():.2e}"
 
 
 @pytest.mark.parametrize("n", [1, 3, 4])

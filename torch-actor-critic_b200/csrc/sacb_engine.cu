@@ -1073,6 +1073,14 @@ int sacb_debug_read(sacb_handle e, const char* name, float* dst, int64_t max_flo
     else if (n == "grad_actor") { src = e->ga; cnt = e->lay.actor_floats; }
     else if (n == "grad_critic") { src = e->gc; cnt = e->lay.critic_floats; }
     else if (n == "loss") { src = e->loss_scalar; cnt = 2; }
+    else if (n == "operand_path") {     // [0] = 1 when precision 3 runs on TMA-fed bf16 shadow operands (csrc/sacb_tma.cuh), [1] = tensor maps
+        if (max_floats < 2) return fail(SACB_ERR_INVALID, "destination too small");
+        CU(cudaSetDevice(e->cfg.device));
+        if (int r = upload_programs(e, nullptr)) return r;
+        dst[0] = (e->bf_tma && e->tf32x3 == 3) ? 1.f : 0.f; dst[1] = (float)e->tmaps.size();
+        if (n_out) *n_out = 2;
+        return 0;
+    }
     else if (n == "rewards") { src = e->rd + (size_t)e->last_parity * 2 * B; cnt = B; }
     else if (n == "done") { src = e->rd + (size_t)e->last_parity * 2 * B + B; cnt = B; }
     else return fail(SACB_ERR_INVALID, "unknown debug array '%s'", name);

@@ -18,6 +18,7 @@
 #pragma once
 
 constexpr int kTmStages = 6;
+constexpr int kTmAcc = 4;                  // independent TMEM accumulators (k16 step mod 4), summed in the epilogue
 constexpr int kTmABytes = kBfM * kBfK * 2, kTmBBytes = kBfN * kBfK * 2;      // 16,384 + 8,192
 constexpr int kTmStageBytes = kTmABytes + kTmBBytes;
 constexpr int kTmMaskOff = kTmStages * kTmStageBytes;                        // 147,456: relu-mask tile [128][68] fp32
@@ -200,6 +201,9 @@ __device__ __forceinline__ void gemm_tile_tma(const Job& jb, int tile, char* pip
                     else tm_load_2d(dB, tmB, j0, k0, full);
                 }
                 if (c == 0) TR(202);
+#ifdef SACB_TRACE_FIRST
+                if (c == 0) { mbar_wait(full, par); TR(210); }          // experiment: time from first issue to first landing
+#endif
             }
             TR(203);
         }
@@ -216,8 +220,11 @@ __device__ __forceinline__ void gemm_tile_tma(const Job& jb, int tile, char* pip
                 const unsigned aA = smem_u32(pipe + s * kTmStageBytes);
                 unsigned long long da = tm_desc(aA, a_rc ? 16u : 8192u, 1024u), db = tm_desc(aA + kTmABytes, b_rc ? 16u : 8192u, 1024u);
                 const int kv = min(kBfK, K - c * kBfK), nk16 = (kv + 15) >> 4;
+                // Four independent accumulators, one per k16 step of a chunk: an MMA into the accumulator the previous one just
+                // wrote waits for that write (~130 cycles each for a 128x64x16 MMA whose math is ~32 cycles -- the K loop
+                // of a K=512 tile measured ~4,500 cycles on one accumulator, as long as the whole operand stream).
                 for (int k16 = 0; k16 < nk16; ++k16) {
-                    bf_mma(cx.tmem, da, db, idesc, (c | k16) ? 1u : 0u);
+                    bf_mma(cx.tmem + (unsigned)(k16 * kBfN), da, db, idesc, c ? 1u : 0u);
                     da += a_step; db += b_step;
                 }
                 t5_commit(bar + 8u * (kTmStages + s));                                 // stage free once these MMAs have read it
@@ -268,22 +275,30 @@ __device__ __forceinline__ void gemm_tile_tma(const Job& jb, int tile, char* pip
     float* s_out = reinterpret_cast<float*>(pipe);             // [128][68]: stages 0-1 (every MMA of the tile has completed)
     {
         const int q4 = warp & 3, half = warp >> 2;
-        unsigned r0[16], r1[16];
-        const unsigned taddr = cx.tmem + ((unsigned)(32 * q4) << 16) + (unsigned)(half * 32);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                     : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]),
-                       "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
-                     : "r"(taddr));
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                     : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
-                       "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
-                     : "r"(taddr + 16u));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int nacc = min(kTmAcc, (min(K, kBfK) + 15) >> 4);          // accumulators the first chunk initialised
+        float v0[16], v1[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
+        for (int a = 0; a < nacc; ++a) {                                 // fixed summation order -> deterministic
+            unsigned r0[16], r1[16];
+            const unsigned taddr = cx.tmem + ((unsigned)(32 * q4) << 16) + (unsigned)(a * kBfN + half * 32);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                         : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]), "=r"(r0[8]),
+                           "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                         : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+                           "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+                         : "r"(taddr + 16u));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { v0[c] += __uint_as_float(r0[c]); v1[c] += __uint_as_float(r1[c]); }
+        }
         float* dst = s_out + (32 * q4 + lane) * kBfPitchRC + half * 32;
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
-            *reinterpret_cast<uint4*>(dst + c) = make_uint4(r0[c], r0[c + 1], r0[c + 2], r0[c + 3]);
-            *reinterpret_cast<uint4*>(dst + 16 + c) = make_uint4(r1[c], r1[c + 1], r1[c + 2], r1[c + 3]);
+            *reinterpret_cast<float4*>(dst + c) = make_float4(v0[c], v0[c + 1], v0[c + 2], v0[c + 3]);
+            *reinterpret_cast<float4*>(dst + 16 + c) = make_float4(v1[c], v1[c + 1], v1[c + 2], v1[c + 3]);
         }
     }
     __syncthreads();

@@ -199,6 +199,7 @@ static int build_tma(sacb_engine* e, cudaStream_t st) {
     CU(cudaMemcpy(e->d_tmaps, e->tmaps.data(), e->tmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(e->d_refresh, &tab, sizeof tab, cudaMemcpyHostToDevice));
     sh.tmaps = e->d_tmaps;
+    { const char* v = getenv("SACB_TMA_PREB"); sh.pre_b = !(v && atoi(v) == 0); }
     e->sh = sh;
     e->n_refresh = nref;
     e->bf_tma = true;
