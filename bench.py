@@ -319,7 +319,9 @@ def run_gpu(args):
     rig.run_updates(args.warmup, False)                             # W untimed warm-up steps
     torch.cuda.synchronize()
     # each repeat times exactly K steps; enough repeats that the clocks sampler sees the GPU under load
-    repeats = args.repeats if args.repeats > 0 else max(1, min(40, math.ceil(4000 / max(args.steps, 1))))
+    # (at least 5, so that the median survives two disturbed repeats: an 8-GPU run of this bench saw two of four repeats
+    # stall for 1.5 s -- some rank's host thread was descheduled between bursts and its peers waited for its gradient)
+    repeats = args.repeats if args.repeats > 0 else max(5, min(40, math.ceil(4000 / max(args.steps, 1))))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
