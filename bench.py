@@ -101,6 +101,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_ready(self, cap_s=8.0):
+        """Block until nvidia-smi has delivered its first sample: its start-up (NVML initialisation: ~1.5 s on an 8-GPU box)
+        holds driver locks, and a rank whose launches stall behind it stalls every peer waiting for its gradients -- keep that
+        out of the timed region."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < cap_s and self.proc.poll() is None:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -325,12 +333,15 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    if world > 1:
+        dist.barrier()
     l0 = eng.launch_count()
     ms, ms_all = timed_region(rig, args.steps, False, world, repeats)      # inputs resident in HBM
     launches = (eng.launch_count() - l0) // repeats
-    clocks = sampler.stop() if rank == 0 else None
     rig.run_updates(min(args.warmup, 2 * UPDATE_EVERY), True)
     ms_e2e, _ = timed_region(rig, args.steps, True, world, max(1, min(repeats, 10)))
+    clocks = sampler.stop() if rank == 0 else None          # (stopped after both timed regions: its teardown takes driver locks too)
     k_ms = kernel_ms(rig)
 
     replicas_identical = None
@@ -388,7 +399,7 @@ def run_gpu(args):
             w2 = Workload("c2")
             rig2 = Rig(w2, 0, local, 3, 0)
             rig2.run_updates(100, False)
-            sam2 = ClockSampler(local); sam2.start()
+            sam2 = ClockSampler(local); sam2.start(); sam2.wait_ready()
             ms2, ms2_all = timed_region(rig2, 200, False, 1, 5)
             clocks2 = sam2.stop()
             k2 = kernel_ms(rig2, 4)
@@ -450,7 +461,7 @@ def run_visual_extra(local, pk, args):
     steps, warm = 30, 5
     sac.update_burst(warm, actor, critic, target, buf, pi_opt, q_opt)
     torch.cuda.synchronize()
-    sam = ClockSampler(local); sam.start()
+    sam = ClockSampler(local); sam.start(); sam.wait_ready()
     ms_all = []
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
