@@ -22,7 +22,7 @@ PHASES = ["gather(first only)", "A.L0+C.L0q1", "A.L1(+heads)+C.L1q1+C.L0q2", "ro
 # unfused program (2A > 16 or the bf16 path): heads and d-pi are GEMM phases of their own
 PHASES_UNFUSED = ["gather(first only)", "A.L0+C.L0q1", "A.L1+C.L1q1+C.L0q2", "A.heads+C.L1q2", "rows_heads", "T.L0", "T.L1",
                   "row_backup", "C.dh1+db1+dW2+lossq", "C.dW1+dW0+db0", "adam_c+polyak", "Cpi.L0", "Cpi.L1", "row_pi", "Cpi.dh1",
-                  "dpi", "row_ghead", "A.dWh+dh2", "A.dW1+dh1", "A.dW0+losspi", "adam_a+gather(k+1)"]
+                  "dpi", "row_ghead", "A.dh2+losspi", "A.dh1", "A.dWh+dW1+dW0", "adam_a+gather(k+1)"]
 
 
 # folded program (csrc/sacb_fold.cuh): 2 first-update-only phases + 8 phases per update (one GPU)

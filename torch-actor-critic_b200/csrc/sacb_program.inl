@@ -20,9 +20,9 @@
 //   P12  min-Q rows (loss_pi parts, dq routing, dh2)
 //   P13  Cpi.dh1 twin (+ d pi as post-product over the action columns of W0)
 //   P14  head-gradient rows (g_mu, g_ls)
-//   P15  A.dWh || dbh || A.dh2
-//   P16  A.dW1 || db1 || A.dh1
-//   P17  A.dW0 || db0 || loss_pi
+//   P15  A.dh2 || loss_pi
+//   P16  A.dh1
+//   P17  A.dWh || dbh || A.dW1 || db1 || A.dW0 || db0        (every K = batch reduction in one phase)
 //   P18  [exchange]  Adam(actor)  ||  gather(k+1)
 //
 // On ONE GPU (mma.sync / FFMA tiles) the Adam step and the Polyak move are applied by the jobs that finish a gradient, in
@@ -247,9 +247,12 @@ static void build_programs(sacb_engine* e) {
             int last = b.phase(); dW1(); dW0();
             return last;
         }
-        b.phase(); dWh(); dh2();
-        b.phase(); dW1(); dh1();
-        b.phase(); dW0(); loss_pi();
+        // Unfused: the dX chain first (dh2: K = 2A, dh1: K = H2 -- short reductions), then ALL weight gradients (reductions over
+        // the batch, K = B: the long tiles) in one phase.  Riding dW_L with the dX through layer L instead made every one of
+        // the three phases as long as a K = B tile (C2, 128x64 tiles: 11.6 + 10.4 + 10.7 us -> 3.5 + 6.5 + 11 us).
+        b.phase(); dh2(); loss_pi();
+        b.phase(); dh1();
+        b.phase(); dWh(); dW1(); dW0();
         if (pf_adam && e->ma && e->va) {
             b.add(l2_prefetch(PA, L.actor_floats, 8)); b.add(l2_prefetch(e->ma, L.actor_floats, 8)); b.add(l2_prefetch(e->va, L.actor_floats, 8));
         }
