@@ -88,8 +88,41 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.nvml, self._stop = None, False
+
+    def _start_nvml(self):
+        """In-process NVML (nvidia_ml_py): the same counters nvidia-smi prints, without spawning a process that initialises
+        NVML for every GPU of the box next to the timed region (on 8-GPU boxes that start-up, and possibly the 20 Hz
+        queries of the CLI, stalled a rank's kernel launches for ~1.5 s at a time -- and with it every peer waiting for
+        that rank's gradients)."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [(pynvml.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"), (pynvml.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"), (pynvml.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")]
+        float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)); reasons(h)            # fail here, not in the thread
+        self.nvml = pynvml
+
+        def loop():
+            while not self._stop:
+                try:
+                    sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    r = int(reasons(h))
+                    self.rows.append([str(self.gpu), str(sm), str(mx), "", ""] + ["Active" if r & b else "Not Active" for b, _ in bits])
+                except Exception:
+                    pass
+                time.sleep(0.05)
+        threading.Thread(target=loop, daemon=True).start()
 
     def start(self):
+        if os.environ.get("SACB_BENCH_SAMPLER", "nvml") == "nvml":
+            try:
+                self._start_nvml()
+                return
+            except Exception:
+                self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -106,14 +139,16 @@ class ClockSampler:
         holds driver locks, and a rank whose launches stall behind it stalls every peer waiting for its gradients -- keep that
         out of the timed region."""
         t0 = time.time()
-        while self.proc is not None and not self.rows and time.time() - t0 < cap_s and self.proc.poll() is None:
+        while not self.rows and time.time() - t0 < cap_s and (self.nvml is not None or (self.proc is not None and self.proc.poll() is None)):
             time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
+        if self.proc is None and self.nvml is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
-        self.proc.terminate()
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -125,7 +160,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampler": "nvml (in-process)" if self.nvml is not None else "nvidia-smi -lms 50"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
