@@ -602,6 +602,49 @@ def test_bf16_tma_operands_match_staged_operands(shape, monkeypatch):
         assert (d > 2e-5).mean() <= 3e-2 and d.max() <= 3 * 2 * 3e-4 * 1.001, f"{key}: {(d > 2e-5).mean():.3%} off, max {d.max():.2e}"
 
 
+@pytest.mark.parametrize("precision", [1, 3])
+def test_packed_ring_gather_matches_struct_of_arrays(precision):
+    """The product's replay ring is the packed `[N, pitch]` record array (ReplayBuffer); most parity tests bind the five
+    separate arrays.  Same transitions, same indices and noise through both layouts must give bit-identical bursts -- in the
+    default kernel (records land through cp.async.bulk, element scatter) and in the tcgen05 / TMA-operand kernel (records
+    land in the idle operand ring, 128-bit scatter + bf16 shadows), Humanoid-sized records (771 floats)."""
+    from torch_actor_critic_b200.engine import Engine, actor_views, critic_views
+    O, A, H, B, N = 376, 17, [512, 512], 1024, 4096
+    rng = np.random.default_rng(21)
+    actor, critic = onp.init_params(O, A, H, rng)
+    arrays = dict(state=rng.standard_normal((N, O)).astype(np.float32), actions=rng.uniform(-1, 1, (N, A)).astype(np.float32),
+                  rewards=rng.standard_normal(N).astype(np.float32), next_state=rng.standard_normal((N, O)).astype(np.float32),
+                  done=rng.random(N) < 0.05)
+    idx = np.stack([rng.choice(N, B, replace=False) for _ in range(3)])
+    eps = rng.standard_normal((3, 2, B, A)).astype(np.float32)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in arrays.items()}
+    pitch = (2 * O + A + 2 + 15) // 16 * 16
+    rec = torch.zeros(N, pitch, device="cuda")
+    rec[:, :O] = t["state"]; rec[:, O:O + A] = t["actions"]; rec[:, O + A] = t["rewards"]
+    rec[:, O + A + 1:2 * O + A + 1] = t["next_state"]; rec[:, 2 * O + A + 1] = t["done"].float()
+    out = {}
+    for packed in (True, False):
+        eng = Engine(O, A, H, batch_size=B, max_burst=4, device=0, act_limit=1.0)
+        eng.set_precision(precision)
+        pa, pc = eng.new_actor_arena(), eng.new_critic_arena()
+        for k, v in actor_views(eng.layout, pa, O, A, H).items():
+            v.copy_(torch.from_numpy(actor[k]))
+        for k, v in critic_views(eng.layout, pc, O, A, H).items():
+            v.copy_(torch.from_numpy(critic[k]))
+        pt = pc.clone()
+        eng.bind_params(pa, pc, pt)
+        eng.bind_adam(eng.new_actor_arena(), eng.new_actor_arena(), 0, eng.new_critic_arena(), eng.new_critic_arena(), 0)
+        if packed:
+            eng.bind_buffer_packed(rec)
+        else:
+            eng.bind_buffer(t["state"], t["actions"], t["rewards"], t["next_state"], t["done"])
+        eng.set_buffer_state(0, N)
+        lq, lp = eng.update(3, idx=idx, eps=eps)
+        out[packed] = (lq.cpu().numpy(), lp.cpu().numpy(), pa.cpu().numpy(), pc.cpu().numpy(), pt.cpu().numpy())
+    for a, b in zip(out[True], out[False]):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("n", [1, 3, 4])
 def test_acting_path_cluster_kernel_matches_oracle(n):
     """`action, _ = actor(state)` per env step (sac/algorithm.py:233): n <= 4 rows run as ONE launch of an 8-CTA
